@@ -1,0 +1,209 @@
+"""
+ORACLE (test infrastructure, NOT product code) -- the surrogate's evaluate side.
+
+Reference followed:
+  OML/train_surrogate.py:34-54   eval_structure_rate: tree gate -> MLP -> inverse Y scaling -> sum
+  OML/train_surrogate.py:72-152  training recipe (runs on the installed scikit-learn; see train())
+  OML/optimize_SA.py:42,102      called as surrogate.eval_rate(all_trans)
+Third-party arithmetic not in the reference tree: scikit-learn's MLPRegressor / DecisionTreeClassifier /
+StandardScaler forward passes (un-pinned upstream; 1.9.0 here).  `eval_rate_faithful` calls sklearn's own
+predict(), `eval_rate_fp64` is the same arithmetic in NumPy from extracted arrays; tests check they agree.
+The reference has no test pinning scores -> goldens are generated here (tests/golden/make_golden.py).
+
+Two arithmetic modes are restated:
+  * fp64  : the reference's (sklearn) arithmetic -- the score oracle (1e-5 relative bar).
+  * fixed : the exact integer arithmetic the CUDA path computes in (DESIGN.md "Arithmetic"):
+            first-layer weights quantised to a power-of-two grid so that the pre-activations are exact int32
+            sums, second layer an exact int64 dot.  Order-independent, hence bit-reproducible.
+"""
+import math
+import numpy as np
+
+
+class SurrogateParams(object):
+    """Plain arrays of a fitted reference-style surrogate."""
+
+    def __init__(self, offsets, W1, b1, w2, b2, y_mean=0.0, y_scale=1.0, tree=None):
+        self.offsets = np.asarray(offsets, dtype=np.int32)          # [K,2] descriptor column -> site offset
+        self.W1 = np.asarray(W1, dtype=np.float64)                  # [K,H]
+        self.b1 = np.asarray(b1, dtype=np.float64)                  # [H]
+        self.w2 = np.asarray(w2, dtype=np.float64).reshape(-1)      # [H]
+        self.b2 = float(np.asarray(b2).reshape(-1)[0])
+        self.y_mean = float(y_mean)
+        self.y_scale = float(y_scale)
+        self.tree = tree                                            # dict(feature,thr,left,right,active) | None
+        self.K, self.H = self.W1.shape
+        assert self.offsets.shape == (self.K, 2)
+
+    @staticmethod
+    def from_sklearn(predictor, y_scaler, classifier, offsets):
+        tree = flatten_tree(classifier) if classifier is not None else None
+        return SurrogateParams(offsets, predictor.coefs_[0], predictor.intercepts_[0], predictor.coefs_[1],
+                               predictor.intercepts_[1], float(y_scaler.mean_[0]), float(y_scaler.scale_[0]),
+                               tree)
+
+    @staticmethod
+    def random_init(offsets, H=20, seed=0, y_mean=0.0, y_scale=1.0):
+        """sklearn's Glorot-uniform init bound sqrt(6/(fan_in+fan_out)) at the reference widths."""
+        rng = np.random.default_rng(seed)
+        K = len(offsets)
+        b = math.sqrt(6.0 / (K + H))
+        W1 = rng.uniform(-b, b, (K, H))
+        b1 = rng.uniform(-b, b, H)
+        b = math.sqrt(6.0 / (H + 1))
+        w2 = rng.uniform(-b, b, H)
+        b2 = rng.uniform(-b, b)
+        return SurrogateParams(offsets, W1, b1, w2, b2, y_mean, y_scale, None)
+
+
+def flatten_tree(classifier):
+    """sklearn DecisionTreeClassifier -> arrays; leaf iff feature < 0; go left iff x[feature] <= thr."""
+    t = classifier.tree_
+    cls = np.asarray(classifier.classes_)
+    leaf_cls = cls[np.argmax(t.value[:, 0, :], axis=1)]
+    return dict(feature=t.feature.astype(np.int32), thr=t.threshold.astype(np.float64),
+                left=t.children_left.astype(np.int32), right=t.children_right.astype(np.int32),
+                active=(leaf_cls == 1.0).astype(np.uint8))
+
+
+def tree_predict(tree, X):
+    """Active flag per row of X ([n, K] 0/1 values)."""
+    n = X.shape[0]
+    node = np.zeros(n, dtype=np.int64)
+    live = tree["feature"][node] >= 0
+    while live.any():
+        idx = np.nonzero(live)[0]
+        nd = node[idx]
+        f = tree["feature"][nd]
+        go_left = X[idx, f] <= tree["thr"][nd]
+        node[idx] = np.where(go_left, tree["left"][nd], tree["right"][nd])
+        live = tree["feature"][node] >= 0
+    return tree["active"][node].astype(bool)
+
+
+def eval_rate_fp64(p, X, normalize=False):
+    """train_surrogate.py:34-54 with extracted arrays.  X = descriptor matrix [n_rows, K]."""
+    X = np.asarray(X, dtype=np.float64)
+    active = tree_predict(p.tree, X) if p.tree is not None else np.ones(len(X), dtype=bool)
+    if not active.any():
+        return 0
+    hidden = np.maximum(X[active] @ p.W1 + p.b1, 0.0)
+    y = hidden @ p.w2 + p.b2
+    rates = y * p.y_scale + p.y_mean
+    return rates.sum() / len(X) if normalize else rates.sum()
+
+
+class FaithfulSurrogate(object):
+    """The reference's surrogate object with its defects 1-3 of SURVEY 9.5 resolved; uses sklearn predict()."""
+
+    def __init__(self, predictor=None, Y_scaler=None, classifier=None):
+        self.predictor, self.Y_scaler, self.classifier = predictor, Y_scaler, classifier
+
+    def eval_structure_rate(self, all_trans, normalize=False):
+        active = self.classifier.predict(all_trans) == 1.0
+        if not active.any():
+            return 0
+        y = self.predictor.predict(all_trans[active, :]).reshape(-1, 1)
+        rates = self.Y_scaler.inverse_transform(y)
+        return np.sum(rates) / len(all_trans) if normalize else np.sum(rates)
+
+    eval_rate = eval_structure_rate
+
+
+def train(all_syms, site_rates, seed=0, max_iter=10000, verbose=False):
+    """train_surrogate.py:72-152 on the installed sklearn.  all_syms: [n_struct*3N, K]; site_rates: [n_struct, N]."""
+    from sklearn import tree
+    from sklearn.neural_network import MLPRegressor
+    from sklearn.model_selection import train_test_split
+    from sklearn.preprocessing import StandardScaler
+    flat = np.transpose(np.tile(site_rates.flatten(), [3, 1])).flatten()
+    y_max = np.max(flat)
+    if y_max == 0.0:
+        raise NameError("No active sites in database.")
+    is_active = (flat > 0.06 * y_max).astype(float)
+    X_reg, Y_reg = all_syms[is_active == 1], flat[is_active == 1]
+    clf = tree.DecisionTreeClassifier(max_depth=30, random_state=0)
+    X_train, _, y_train, _ = train_test_split(all_syms, is_active, random_state=0)
+    clf.fit(X_train, y_train)
+    scaler = StandardScaler(with_mean=True, with_std=True)
+    scaler.fit(Y_reg.reshape(-1, 1))
+    Y = scaler.transform(Y_reg.reshape(-1, 1)).flatten()
+    mlp = MLPRegressor(activation="relu", verbose=verbose, learning_rate_init=0.0001, alpha=0.1,
+                       hidden_layer_sizes=(20,), max_iter=max_iter, tol=0.00001, random_state=seed)
+    mlp.fit(X_reg, Y)
+    return FaithfulSurrogate(mlp, scaler, clf)
+
+
+# ---- fixed-point arithmetic (the CUDA path's arithmetic) ------------------------------------------------
+
+SPLIT_BITS = 20          # big integer sums are carried as hi*2^20 + lo, 0 <= lo < 2^20
+
+
+def ceil_log2(x):
+    """Smallest integer e with 2**e >= x, exact (no floating log)."""
+    m, e = math.frexp(x)            # x = m * 2**e, 0.5 <= m < 1
+    return e - 1 if m == 0.5 else e
+
+
+def quantize(p):
+    """Power-of-two fixed-point grids for layer 1 (int32 pre-activations) and layer 2 (int64 dot)."""
+    Hp = (p.H + 3) // 4 * 4
+    bound = float(np.max(np.abs(p.b1) + np.abs(p.W1).sum(0)))
+    bound = max(bound, 2.0 ** -100)
+    e_h = ceil_log2(bound) - 30          # |h|/2^e_h <= 2^30 (+ (K+1)/2 rounding slack < 2^31)
+    w_bits = 31 - ceil_log2(float(Hp))          # |A_r| <= Hp * 2^w_bits * 2^31 <= 2^62
+    wmax = max(float(np.max(np.abs(p.w2))), 2.0 ** -100)
+    e_w = ceil_log2(wmax) - w_bits
+    W1q = np.zeros((p.K, Hp), dtype=np.int32)
+    b1q = np.zeros(Hp, dtype=np.int32)
+    w2q = np.zeros(Hp, dtype=np.int32)
+    W1q[:, :p.H] = np.rint(np.ldexp(p.W1, -e_h)).astype(np.int64)
+    b1q[:p.H] = np.rint(np.ldexp(p.b1, -e_h)).astype(np.int64)
+    w2q[:p.H] = np.rint(np.ldexp(p.w2, -e_w)).astype(np.int64)
+    assert int(np.abs(b1q.astype(np.int64)).max() + np.abs(W1q.astype(np.int64)).sum(0).max()) < 2 ** 31
+    return dict(Hp=Hp, e_h=e_h, e_w=e_w, W1q=W1q, b1q=b1q, w2q=w2q, c=math.ldexp(1.0, e_h + e_w))
+
+
+def split(a):
+    """Python int / int64 array -> (hi, lo) with a = hi*2^20 + lo, 0 <= lo < 2^20 (floor semantics)."""
+    return a >> SPLIT_BITS, a & ((1 << SPLIT_BITS) - 1)
+
+
+def to_real(hi, lo):
+    """The pinned conversion of a split sum to fp64: fl(fl(hi)*2^20 + fl(lo))."""
+    return np.float64(hi) * np.float64(2.0 ** SPLIT_BITS) + np.float64(lo)
+
+
+def real_from_sums(p, q, hi, lo, n_act):
+    """OF = sigma*(c*S + b2*n) + mu*n with the operation order pinned (no fused multiply-add)."""
+    S = to_real(hi, lo)
+    n = np.float64(n_act)
+    t3 = np.float64(q["c"]) * S + np.float64(p.b2) * n
+    return np.float64(p.y_scale) * t3 + np.float64(p.y_mean) * n
+
+
+def preact_fixed(p, q, x, d):
+    """Exact int32 pre-activations hq[N, Hp] of one structure."""
+    N = d * d
+    r = np.arange(N)
+    r1, r2 = r % d, r // d
+    idx = ((r2[:, None] + p.offsets[None, :, 1]) % d) * d + (r1[:, None] + p.offsets[None, :, 0]) % d
+    X = np.asarray(x)[idx].astype(np.int64)                       # [N, K]
+    return (X @ q["W1q"].astype(np.int64) + q["b1q"].astype(np.int64)).astype(np.int32), X
+
+
+def row_sums_fixed(q, hq):
+    """A_r = sum_j w2q_j * relu(hq_rj), exact int64."""
+    return (np.maximum(hq.astype(np.int64), 0) * q["w2q"].astype(np.int64)).sum(1)
+
+
+def score_fixed(p, q, x, d):
+    """(OF fp64, hi, lo, n_active, gate[N]) of one structure in the CUDA path's arithmetic."""
+    hq, X = preact_fixed(p, q, x, d)
+    A = row_sums_fixed(q, hq)
+    gate = tree_predict(p.tree, X) if p.tree is not None else np.ones(len(A), dtype=bool)
+    hi = int(sum(int(a) >> SPLIT_BITS for a in A[gate]))
+    lo = int(sum(int(a) & ((1 << SPLIT_BITS) - 1) for a in A[gate]))
+    hi, lo = hi + (lo >> SPLIT_BITS), lo & ((1 << SPLIT_BITS) - 1)
+    n_act = int(gate.sum())
+    return float(real_from_sums(p, q, hi, lo, n_act)), hi, lo, n_act, gate

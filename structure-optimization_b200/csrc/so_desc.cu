@@ -1,0 +1,359 @@
+// so_desc.cu -- integer descriptor kernels on bit-packed occupancies (sm_100a).
+//
+// Replaces the NetworkX passes of the reference:
+//   Ni-neighbour count pass            OML/LSC_cat.py:186-196, OML/NH3_cat.py:188-198
+//   LSC site typing                    OML/LSC_cat.py:176-220
+//   NH3 site typing (19 types)         OML/NH3_cat.py:169-396, export map :421
+// The VF2 sub-graph matches collapse to closed-form local rules on the layer-3 bits (checked
+// against a literal NetworkX evaluation in tests/test_oracle_types.py).  Each chain's bit-plane is staged in
+// shared memory; histograms are reduced with warp ballots + popc.
+#include "so_internal.cuh"
+
+// ring order: consecutive entries are mutually adjacent
+__device__ __constant__ int8_t c_ring1[6] = {1, 0, -1, -1, 0, 1};
+__device__ __constant__ int8_t c_ring2[6] = {0, 1, 1, 0, -1, -1};
+
+// ---- pack / unpack / randomize ------------------------------------------------------------------------
+__global__ void pack_kernel(const uint8_t *__restrict__ occ, uint32_t *__restrict__ bits, long long n, int N, int W,
+                            unsigned long long *flag) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * W) return;
+  long long chain = t / W;
+  int w = (int)(t - chain * W);
+  const uint8_t *src = occ + chain * N + w * 32;
+  int lim = min(32, N - w * 32);
+  uint32_t word = 0;
+  bool bad = false;
+  for (int b = 0; b < lim; ++b) {
+    uint8_t v = src[b];
+    bad |= (v > 1);
+    word |= (uint32_t)(v & 1) << b;
+  }
+  bits[t] = word;
+  if (bad) atomicOr(flag, 1ULL);
+}
+
+__global__ void unpack_kernel(const uint32_t *__restrict__ bits, uint8_t *__restrict__ occ, long long n, int N, int W) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * (long long)N) return;
+  long long chain = t / N;
+  int v = (int)(t - chain * N);
+  occ[t] = (bits[chain * W + (v >> 5)] >> (v & 31)) & 1;
+}
+
+// Bernoulli(p) bits: word w of chain c uses Philox counters (w, i, c_lo, c_hi), i = 0..7 (32 draws);
+// p per chain = coverage, or a uniform draw from counter (0xffffffff, 0, c_lo, c_hi) when coverage < 0.
+__global__ void randomize_kernel(uint32_t *bits, long long n, int N, int W, unsigned long long seed, double coverage) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * W) return;
+  long long chain = t / W;
+  int w = (int)(t - chain * W);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c2 = (uint32_t)chain, c3 = (uint32_t)((unsigned long long)chain >> 32);
+  uint32_t o[4];
+  double p = coverage;
+  if (coverage < 0) {
+    philox4x32_10(0xffffffffu, 0u, c2, c3, k0, k1, o);
+    p = (double)o[0] * (1.0 / 4294967296.0);
+  }
+  // threshold on 32-bit draws: bit = draw < p * 2^32
+  double thr_d = p * 4294967296.0;
+  unsigned long long thr = thr_d >= 4294967296.0 ? 4294967296ULL : (unsigned long long)thr_d;
+  uint32_t word = 0;
+  for (int i = 0; i < 8; ++i) {
+    philox4x32_10((uint32_t)w, (uint32_t)i, c2, c3, k0, k1, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) word |= (uint32_t)((unsigned long long)o[j] < thr) << (i * 4 + j);
+  }
+  int lim = N - w * 32;
+  if (lim < 32) word &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
+  bits[t] = word;
+}
+
+// ---- closed-form typing rules -----------------------------------------------------------------------
+struct L3Info {
+  int x, c6, adj;   // occupancy, Ni neighbours, "two ring-adjacent vacancies"
+};
+
+__device__ __forceinline__ L3Info l3_info(const BitView &b, int i1, int i2) {
+  L3Info r;
+  r.x = b.at(i1, i2);
+  int ring = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ring |= b.at(i1 + c_ring1[k], i2 + c_ring2[k]) << k;
+  r.c6 = __popc(ring);
+  int vac = (~ring) & 63;
+  int rot = ((vac << 1) | (vac >> 5)) & 63;
+  r.adj = (vac & rot) != 0;
+  return r;
+}
+__device__ __forceinline__ int lsc_type_of(const L3Info &s) {
+  if (!s.x) return 0;
+  if (s.c6 == 6) return 1;
+  if (s.c6 == 4 && s.adj) return 2;
+  return 0;
+}
+// NH3 base type of a layer-3 site: Ni -> 3 / 5 / 4, vacancy -> 6 (refined by l3_full)
+__device__ __forceinline__ int nh3_t3_of(const L3Info &s) {
+  if (!s.x) return 6;
+  if (s.c6 == 6) return 3;
+  if (s.c6 == 4 && s.adj) return 5;
+  return 4;
+}
+// number of Ni under layer-4 atom (j1,j2): sites (0,-1),(1,-1),(0,0)
+__device__ __forceinline__ int n_tri4(const BitView &b, int j1, int j2) {
+  return b.at(j1, j2 - 1) + b.at(j1 + 1, j2 - 1) + b.at(j1, j2);
+}
+// number of Ni over layer-2 atom (k1,k2): sites (1,-1),(0,0),(1,0)
+__device__ __forceinline__ int n_tri2(const BitView &b, int k1, int k2) {
+  return b.at(k1 + 1, k2 - 1) + b.at(k1, k2) + b.at(k1 + 1, k2);
+}
+__device__ __forceinline__ int nh3_l4_type(const BitView &b, int j1, int j2) {
+  int n = n_tri4(b, j1, j2);
+  if (n == 1) return 12;
+  if (n == 2) return 14;
+  if (n == 0) return 0;
+  int e = 0;
+  int t;
+  t = nh3_t3_of(l3_info(b, j1, j2 - 1)); e += (t == 4 || t == 5);
+  t = nh3_t3_of(l3_info(b, j1 + 1, j2 - 1)); e += (t == 4 || t == 5);
+  t = nh3_t3_of(l3_info(b, j1, j2)); e += (t == 4 || t == 5);
+  return e == 0 ? 1 : (e == 1 ? 17 : 16);
+}
+__device__ __forceinline__ int nh3_l2_type(const BitView &b, int k1, int k2) {
+  int n = n_tri2(b, k1, k2);
+  if (n == 0) return 8;
+  if (n == 2) return 15;
+  if (n == 1) return 0;
+  int ntop = 0, nedge = 0, t;
+  t = nh3_t3_of(l3_info(b, k1 + 1, k2 - 1)); ntop += (t == 3); nedge += (t == 5);
+  t = nh3_t3_of(l3_info(b, k1, k2)); ntop += (t == 3); nedge += (t == 5);
+  t = nh3_t3_of(l3_info(b, k1 + 1, k2)); ntop += (t == 3); nedge += (t == 5);
+  if (ntop == 2 && nedge == 1) return 18;
+  if (ntop == 1 && nedge == 2) return 19;
+  return 2;
+}
+// full layer-3 type incl. the vacancy refinements 10 / 11 / 9
+__device__ __forceinline__ int nh3_l3_type(const BitView &b, int i1, int i2, const L3Info &s, const int32_t *h5_ptr,
+                                           const int32_t *h5_idx) {
+  int t = nh3_t3_of(s);
+  if (t != 6) return t;
+  // layer-4 atoms above: (0,0), (-1,1), (0,1)
+  int na = n_tri4(b, i1, i2), nb = n_tri4(b, i1 - 1, i2 + 1), nc = n_tri4(b, i1, i2 + 1);
+  if (na == 2 || nb == 2 || nc == 2) return 11;
+  if (na == 1 || nb == 1 || nc == 1) return 10;
+  int d = b.d;
+  int v = i2 * d + i1;
+  for (int p = h5_ptr[v]; p < h5_ptr[v + 1]; ++p) {
+    int j = h5_idx[p];
+    int k2 = j / d, k1 = j - k2 * d;
+    if (n_tri2(b, k1, k2) == 2) return 9;
+  }
+  return 6;
+}
+__device__ __forceinline__ int nh3_l1_type(const BitView &b, int m1, int m2) {
+  // layer-2 atoms above: (-1,0), (0,-1), (0,0); type 8 <=> n_tri2 == 0, None <=> n_tri2 == 1
+  int a = n_tri2(b, m1 - 1, m2), c = n_tri2(b, m1, m2 - 1), e = n_tri2(b, m1, m2);
+  int n8 = (a == 0) + (c == 0) + (e == 0);
+  int n0 = (a == 1) + (c == 1) + (e == 1);
+  if (n8 == 3) return 7;
+  if (n8 == 2 && n0 == 1) return 13;
+  return 0;
+}
+__device__ __forceinline__ int nh3_export_code(int t) {
+  // {1:1, 3:2, 5:3, 16:4, 17:5, 18:6, 19:7}  (OML/NH3_cat.py:421)
+  switch (t) {
+    case 1: return 1;
+    case 3: return 2;
+    case 5: return 3;
+    case 16: return 4;
+    case 17: return 5;
+    case 18: return 6;
+    case 19: return 7;
+    default: return 0;
+  }
+}
+
+// ---- full-structure descriptors: one block per chain ------------------------------------------------
+__global__ void __launch_bounds__(256) descriptors_kernel(const uint32_t *__restrict__ bits, int d, int N, int W,
+                                                          const int32_t *__restrict__ h5_ptr,
+                                                          const int32_t *__restrict__ h5_idx, uint8_t *c6_out,
+                                                          uint8_t *lsc_out, uint8_t *nh3_out, int32_t *lsc_hist,
+                                                          int32_t *nh3_hist, int32_t *nh3_exp, int want_nh3) {
+  extern __shared__ uint32_t s_bits[];
+  __shared__ int s_hist[24];
+  const long long chain = blockIdx.x;
+  for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = bits[chain * W + w];
+  if (threadIdx.x < 24) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  BitView b{s_bits, d, -1};
+  const int lane = threadIdx.x & 31;
+  int cnt_nh3 = 0;   // lane t counts NH3 type t (t < 20)
+  int cnt_lsc = 0;   // lane t counts LSC type t (t < 3)
+  const int first = want_nh3 ? N : 3 * N, last = want_nh3 ? 5 * N : 4 * N;
+  for (int base = first; base < last; base += blockDim.x) {
+    int n = base + threadIdx.x;
+    int t = 255, tl = 255;
+    if (n < last) {
+      int layer = n / N;
+      int v = n - layer * N;
+      int i2 = v / d, i1 = v - i2 * d;
+      if (layer == 3) {
+        L3Info s = l3_info(b, i1, i2);
+        tl = lsc_type_of(s);
+        if (c6_out) c6_out[chain * N + v] = (uint8_t)s.c6;
+        if (lsc_out) lsc_out[chain * N + v] = (uint8_t)tl;
+        if (want_nh3) t = nh3_l3_type(b, i1, i2, s, h5_ptr, h5_idx);
+      } else if (layer == 4) {
+        t = nh3_l4_type(b, i1, i2);
+      } else if (layer == 2) {
+        t = nh3_l2_type(b, i1, i2);
+      } else {
+        t = nh3_l1_type(b, i1, i2);
+      }
+      if (want_nh3 && nh3_out) nh3_out[chain * 5LL * N + n] = (uint8_t)t;
+    }
+    if (want_nh3) {
+#pragma unroll
+      for (int tt = 0; tt < 20; ++tt) {
+        unsigned m = __ballot_sync(SO_FULL, t == tt);
+        if (lane == tt) cnt_nh3 += __popc(m);
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < 3; ++tt) {
+      unsigned m = __ballot_sync(SO_FULL, tl == tt);
+      if (lane == tt) cnt_lsc += __popc(m);
+    }
+  }
+  if (lane < 20 && cnt_nh3) atomicAdd(&s_hist[lane], cnt_nh3);
+  if (lane < 3 && cnt_lsc) atomicAdd(&s_hist[20 + lane], cnt_lsc);
+  __syncthreads();
+  if (threadIdx.x < 20 && want_nh3) {
+    int hv = s_hist[threadIdx.x] + (threadIdx.x == 0 ? N : 0);   // layer 0 is always None
+    if (nh3_hist) nh3_hist[chain * 20 + threadIdx.x] = hv;
+  }
+  if (threadIdx.x < 3 && lsc_hist) lsc_hist[chain * 3 + threadIdx.x] = s_hist[20 + threadIdx.x];
+  if (threadIdx.x == 0 && want_nh3 && nh3_exp) {
+    int e1 = s_hist[1], e2 = s_hist[3], e3 = s_hist[5], e4 = s_hist[16], e5 = s_hist[17], e6 = s_hist[18],
+        e7 = s_hist[19];
+    int32_t *o = nh3_exp + chain * 8;
+    o[0] = 5 * N - (e1 + e2 + e3 + e4 + e5 + e6 + e7);
+    o[1] = e1; o[2] = e2; o[3] = e3; o[4] = e4; o[5] = e5; o[6] = e6; o[7] = e7;
+  }
+}
+
+// ---- per-flip descriptor deltas: one warp per chain, one affected node per lane -----------------------
+struct AffTable {
+  int n;
+  int8_t layer[32], o1[32], o2[32];
+};
+
+static AffTable build_aff_table() {
+  // layer-3 sites within one ring of the flip; layer-4 / layer-2 atoms whose triangle touches them
+  static const int ring[7][2] = {{0, 0}, {1, 0}, {0, 1}, {-1, 1}, {-1, 0}, {0, -1}, {1, -1}};
+  static const int up34[3][2] = {{0, 0}, {-1, 1}, {0, 1}};
+  static const int dn32[3][2] = {{-1, 0}, {0, 0}, {-1, 1}};
+  AffTable t;
+  t.n = 0;
+  auto add = [&](int layer, int a, int b) {
+    for (int i = 0; i < t.n; ++i)
+      if (t.layer[i] == layer && t.o1[i] == a && t.o2[i] == b) return;
+    t.layer[t.n] = (int8_t)layer; t.o1[t.n] = (int8_t)a; t.o2[t.n] = (int8_t)b; ++t.n;
+  };
+  for (auto &s : ring) add(3, s[0], s[1]);
+  for (auto &s : ring) for (auto &u : up34) add(4, s[0] + u[0], s[1] + u[1]);
+  for (auto &s : ring) for (auto &u : dn32) add(2, s[0] + u[0], s[1] + u[1]);
+  return t;   // 7 + 12 + 12 = 31 entries
+}
+
+__global__ void __launch_bounds__(256) flip_delta_kernel(const uint32_t *__restrict__ bits, long long n, int d, int N,
+                                                         int W, const int32_t *__restrict__ sites, AffTable aff,
+                                                         int32_t *d_lsc, int32_t *d_nh3_exp) {
+  const int lane = threadIdx.x & 31;
+  long long chain = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (chain >= n) return;
+  const uint32_t *w = bits + chain * W;
+  int f = sites[chain];
+  int f2 = f / d, f1 = f - f2 * d;
+  int code0 = -1, code1 = -1, lsc0 = -1, lsc1 = -1;
+  int node = -1 - lane;   // unique negative id for idle lanes
+  if (lane < aff.n) {
+    int layer = aff.layer[lane];
+    int i1 = wrap(f1 + aff.o1[lane], d), i2 = wrap(f2 + aff.o2[lane], d);
+    node = layer * N + i2 * d + i1;
+  }
+  // aliasing on tiny lattices: only the lowest lane of equal nodes counts
+  unsigned same = __match_any_sync(SO_FULL, node);
+  bool leader = (lane < aff.n) && ((__ffs(same) - 1) == lane);
+  if (leader) {
+    int layer = aff.layer[lane];
+    int v = node - layer * N;
+    int i2 = v / d, i1 = v - i2 * d;
+    BitView b0{w, d, -1}, b1{w, d, f};
+    if (layer == 3) {
+      L3Info s0 = l3_info(b0, i1, i2), s1 = l3_info(b1, i1, i2);
+      lsc0 = lsc_type_of(s0); lsc1 = lsc_type_of(s1);
+      code0 = nh3_export_code(nh3_t3_of(s0)); code1 = nh3_export_code(nh3_t3_of(s1));
+    } else if (layer == 4) {
+      code0 = nh3_export_code(nh3_l4_type(b0, i1, i2)); code1 = nh3_export_code(nh3_l4_type(b1, i1, i2));
+    } else {
+      code0 = nh3_export_code(nh3_l2_type(b0, i1, i2)); code1 = nh3_export_code(nh3_l2_type(b1, i1, i2));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    int dlt = __popc(__ballot_sync(SO_FULL, code1 == t)) - __popc(__ballot_sync(SO_FULL, code0 == t));
+    if (lane == t && d_nh3_exp) d_nh3_exp[chain * 8 + t] = dlt;
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    int dlt = __popc(__ballot_sync(SO_FULL, lsc1 == t)) - __popc(__ballot_sync(SO_FULL, lsc0 == t));
+    if (lane == t && d_lsc) d_lsc[chain * 3 + t] = dlt;
+  }
+}
+
+// ---- launch wrappers -------------------------------------------------------------------------------------
+int so_launch_pack(const uint8_t *occ_dev, uint32_t *bits_dev, int64_t n, int N, int W, unsigned long long *flag,
+                   cudaStream_t st) {
+  long long total = n * W;
+  if (total == 0) return SO_OK;
+  pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(occ_dev, bits_dev, n, N, W, flag);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_unpack(const uint32_t *bits_dev, uint8_t *occ_dev, int64_t n, int N, int W, cudaStream_t st) {
+  long long total = n * (long long)N;
+  if (total == 0) return SO_OK;
+  unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bits_dev, occ_dev, n, N, W);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_randomize(uint32_t *bits_dev, int64_t n, int N, int W, uint64_t seed, double coverage, cudaStream_t st) {
+  long long total = n * W;
+  if (total == 0) return SO_OK;
+  randomize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bits_dev, n, N, W, seed, coverage);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_descriptors(const so_lattice *lat, const uint32_t *bits_dev, int64_t n, uint8_t *c6, uint8_t *lsc_type,
+                          uint8_t *nh3_type, int32_t *lsc_hist, int32_t *nh3_hist, int32_t *nh3_exp, cudaStream_t st) {
+  if (n == 0) return SO_OK;
+  int want_nh3 = (nh3_type || nh3_hist || nh3_exp) ? 1 : 0;
+  int threads = lat->N >= 256 ? 256 : ((lat->N + 31) / 32) * 32;
+  descriptors_kernel<<<(unsigned)n, threads, lat->W * sizeof(uint32_t), st>>>(
+      bits_dev, lat->d, lat->N, lat->W, lat->h5_ptr_dev, lat->h5_idx_dev, c6, lsc_type, nh3_type, lsc_hist, nh3_hist,
+      nh3_exp, want_nh3);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_flip_delta(const so_lattice *lat, const uint32_t *bits_dev, int64_t n, const int32_t *sites_dev,
+                         int32_t *d_lsc, int32_t *d_nh3_exp, cudaStream_t st) {
+  if (n == 0) return SO_OK;
+  static const AffTable aff = build_aff_table();
+  long long threads = n * 32;
+  flip_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(bits_dev, n, lat->d, lat->N, lat->W, sites_dev,
+                                                                       aff, d_lsc, d_nh3_exp);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}

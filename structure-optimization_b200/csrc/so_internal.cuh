@@ -1,0 +1,176 @@
+// so_internal.cuh -- shared declarations of the sm_100a hot path (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/so_b200.h"
+
+#define SO_SPLIT_BITS 20
+#define SO_SPLIT_MASK ((1LL << SO_SPLIT_BITS) - 1)
+#define SO_FULL 0xffffffffu
+
+void so_set_error(const char *fmt, ...);
+#define SO_CUDA(call)                                                                           \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      so_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));      \
+      return SO_ECUDA;                                                                          \
+    }                                                                                           \
+  } while (0)
+
+struct so_lattice {
+  int d, N, W, kind, device;
+  std::vector<int32_t> rowptr, col;     // host CSR of the 5N-node graph
+  std::vector<double> pos;              // raw positions [5N][3]
+  double cell[4];
+  int32_t *h5_ptr_dev, *h5_idx_dev;     // NH3 type-9 pair table (layer-3 site -> layer-2 atoms, non-periodic)
+};
+
+struct so_surrogate {
+  so_lattice *lat;
+  int device;
+  int K, H, Hp, HP4, e_h, e_w, gated, n_tree;
+  double c, b2, y_mean, y_scale;
+  int32_t *offs_dev;                    // [K] packed (o2 << 16) | (o1 & 0xffff)
+  int32_t *W1q_dev, *b1q_dev, *w2q_dev; // [K][Hp], [Hp], [Hp]
+  double *W1d_dev, *b1d_dev, *w2d_dev;  // fp64 originals [K][H], [H], [H] (exact guard)
+  int32_t *t_feature_dev, *t_left_dev, *t_right_dev;
+  double *t_thr_dev;
+  uint8_t *t_active_dev;
+  std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
+};
+
+struct so_chains {
+  so_lattice *lat;
+  int device;
+  so_surrogate *sur;
+  int64_t n_chains;
+  uint32_t *bits_dev;                   // [n_chains][W]
+  int32_t *hq_dev;                      // [n_chains][N][Hp]
+  long long *hi_dev, *lo_dev;           // objective sums: hi*2^20 + lo
+  int32_t *nact_dev;                    // active sites (gated) or N
+  double *tscale_dev;
+  unsigned long long *counters_dev;     // [0]=work counter [1]=accepted [2]=guard fired [3]=invalid flag [4]=swaps
+  double *xch_scratch;                  // exchange scratch [xch_cap]
+  int64_t xch_cap;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+};
+
+// ---- device-side views ------------------------------------------------------------------------------
+struct SurView {
+  int K, Hp, HP4, gated;
+  double c, b2, y_mean, y_scale;
+  const int32_t *offs;
+  const int32_t *W1q, *b1q, *w2q;
+  const double *W1d, *b1d, *w2d;
+  int H;
+  const int32_t *t_feature, *t_left, *t_right;
+  const double *t_thr;
+  const uint8_t *t_active;
+};
+
+struct SaParams {
+  int d, N, W;
+  long long n_chains;
+  uint32_t *bits;
+  int32_t *hq;
+  long long *hi, *lo;
+  int32_t *nact;
+  const double *tscale;
+  const double *temps;                  // [n_steps] device
+  long long step0, n_steps;
+  unsigned long long seed;
+  long long chain_id0;
+  const int32_t *proposals;             // device or null
+  const float *uniforms;
+  uint8_t *accept_out;
+  int exact_guard;
+  double guard_tol;
+  int variant;                          // 0 auto, 1 force the row-per-lane (gated) kernel
+  unsigned long long *counters;
+  SurView sv;
+};
+
+inline SurView make_view(const so_surrogate *s) {
+  SurView v;
+  v.K = s->K; v.Hp = s->Hp; v.HP4 = s->HP4; v.gated = s->gated; v.H = s->H;
+  v.c = s->c; v.b2 = s->b2; v.y_mean = s->y_mean; v.y_scale = s->y_scale;
+  v.offs = s->offs_dev; v.W1q = s->W1q_dev; v.b1q = s->b1q_dev; v.w2q = s->w2q_dev;
+  v.W1d = s->W1d_dev; v.b1d = s->b1d_dev; v.w2d = s->w2d_dev;
+  v.t_feature = s->t_feature_dev; v.t_left = s->t_left_dev; v.t_right = s->t_right_dev;
+  v.t_thr = s->t_thr_dev; v.t_active = s->t_active_dev;
+  return v;
+}
+
+// ---- launch wrappers (defined in the kernel translation units) ----------------------------------------
+int so_launch_pack(const uint8_t *occ_dev, uint32_t *bits_dev, int64_t n, int N, int W, unsigned long long *flag,
+                   cudaStream_t st);
+int so_launch_unpack(const uint32_t *bits_dev, uint8_t *occ_dev, int64_t n, int N, int W, cudaStream_t st);
+int so_launch_randomize(uint32_t *bits_dev, int64_t n, int N, int W, uint64_t seed, double coverage, cudaStream_t st);
+int so_launch_descriptors(const so_lattice *lat, const uint32_t *bits_dev, int64_t n, uint8_t *c6, uint8_t *lsc_type,
+                          uint8_t *nh3_type, int32_t *lsc_hist, int32_t *nh3_hist, int32_t *nh3_exp, cudaStream_t st);
+int so_launch_flip_delta(const so_lattice *lat, const uint32_t *bits_dev, int64_t n, const int32_t *sites_dev,
+                         int32_t *d_lsc, int32_t *d_nh3_exp, cudaStream_t st);
+int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
+                    long long *hi, long long *lo, int32_t *nact, cudaStream_t st);
+int so_launch_objective(const so_surrogate *s, const long long *hi, const long long *lo, const int32_t *nact, int64_t n,
+                        double *of_dev, cudaStream_t st);
+int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_dev, uint8_t *active_dev,
+                        double *rate_dev, cudaStream_t st);
+int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st);
+int so_launch_apply_flips(const so_chains *c, int64_t n, const int64_t *chains_dev, const int32_t *sites_dev,
+                          cudaStream_t st);
+int so_launch_best(const so_chains *c, int64_t chain_id0, void *record_dev, cudaStream_t st);
+int so_launch_exchange(const so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, int parity, uint64_t seed,
+                       int64_t round, double t_ref, const double *of_all, double *tscale_all, double *scratch,
+                       unsigned long long *n_swapped, cudaStream_t st);
+
+#ifdef __CUDACC__
+// ---- device helpers ----------------------------------------------------------------------------------
+
+// The pinned fp64 conversion of exact integer sums (oracle/surrogate.py real_from_sums): no fused ops.
+__device__ __forceinline__ double so_real(double c, double b2, double sigma, double mu, long long hi, long long lo,
+                                          int n) {
+  double S = __dadd_rn(__dmul_rn(__ll2double_rn(hi), 1048576.0), __ll2double_rn(lo));
+  double nn = (double)n;
+  double t3 = __dadd_rn(__dmul_rn(c, S), __dmul_rn(b2, nn));
+  return __dadd_rn(__dmul_rn(sigma, t3), __dmul_rn(mu, nn));
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ int wrap(int v, int d) {   // valid for -d <= v < 2d
+  v += (v < 0) ? d : 0;
+  v -= (v >= d) ? d : 0;
+  return v;
+}
+
+// bit view of one chain's occupancy with an optional virtual flip
+struct BitView {
+  const uint32_t *w;
+  int d;
+  int flip;   // site index whose bit reads inverted, or -1
+  __device__ __forceinline__ int site(int v) const { return ((w[v >> 5] >> (v & 31)) & 1) ^ (v == flip); }
+  __device__ __forceinline__ int at(int i1, int i2) const { return site(wrap(i2, d) * d + wrap(i1, d)); }
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SO_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SO_FULL, v); }
+#endif

@@ -1,0 +1,338 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Integer/byte/index work must be bit-exact; scores within 1e-5 relative of the fp64 reference arithmetic."""
+import os
+import numpy as np
+import pytest
+
+from oracle import lattice as L, site_types as ST, surrogate as S, sa as SA, philox
+import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from so_b200 import engine
+    return engine
+
+
+# ---- lattice ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [4, 5, 12])
+def test_lattice_tables(eng, d):
+    lat = eng.Lattice(d, "NH3")
+    rowptr, col = lat.csr()
+    rp, cl = L.neighbour_csr(d)
+    assert (rowptr == rp).all()
+    for i in range(5 * d * d):
+        assert set(col[rowptr[i]:rowptr[i + 1]].tolist()) == set(cl[rp[i]:rp[i + 1]].tolist())
+    pos, cell = lat.positions()
+    np.testing.assert_allclose(pos, L.slab_positions(d), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cell, L.cell_vectors(d), rtol=0, atol=1e-12)
+
+
+def test_lattice_rejects_tiny(eng):
+    with pytest.raises(ValueError):
+        eng.Lattice(3, "LSC")
+
+
+# ---- occupancy -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [5, 12, 16])
+def test_occupancy_roundtrip(eng, d):
+    lat = eng.Lattice(d, "LSC")
+    n = 37
+    ch = eng.Chains(lat, n)
+    assert (ch.get_occupancy() == 1).all()                      # all atoms present (LSC_cat.py:50)
+    x = Hp.random_structures(n, d * d, seed=d)
+    ch.set_occupancy(x)
+    assert (ch.get_occupancy() == x).all()
+    assert (ch.get_bits() == eng.pack_bits(x)).all()
+    ch.set_bits(eng.pack_bits(x[::-1].copy()))
+    assert (ch.get_occupancy() == x[::-1]).all()
+    ch.set_occupancy(x[3:5], chain0=10)                         # ragged sub-range
+    assert (ch.get_occupancy(10, 2) == x[3:5]).all()
+    bad = x.copy()
+    bad[2, 7] = 2
+    with pytest.raises(NameError):
+        ch.set_occupancy(bad)
+    with pytest.raises(ValueError):
+        ch.set_occupancy(x, chain0=1)                           # runs past the end
+
+
+def test_flip(eng):
+    d = 12
+    lat = eng.Lattice(d, "LSC")
+    ch = eng.Chains(lat, 4)
+    x = Hp.random_structures(4, 144, seed=1)
+    ch.set_occupancy(x)
+    ch.flip([0, 0, 3, 2, 0], [5, 6, 143, 0, 5])                  # site 5 of chain 0 toggles twice
+    y = x.copy()
+    for c, s in zip([0, 0, 3, 2, 0], [5, 6, 143, 0, 5]):
+        y[c, s] ^= 1
+    assert (ch.get_occupancy() == y).all()
+    with pytest.raises(ValueError):
+        ch.flip([0], [144])
+
+
+def test_randomize_statistics(eng):
+    lat = eng.Lattice(12, "LSC")
+    ch = eng.Chains(lat, 2048)
+    ch.randomize(seed=3, coverage=0.5)
+    x = ch.get_occupancy()
+    assert abs(x.mean() - 0.5) < 0.01
+    ch.randomize(seed=3, coverage=0.5)
+    assert (ch.get_occupancy() == x).all()                      # counter-based: same seed, same bits
+    ch.randomize(seed=4, coverage=None)
+    cov = ch.get_occupancy().mean(1)
+    assert cov.std() > 0.2 and 0.4 < cov.mean() < 0.6           # per-chain coverage ~ U(0,1)
+
+
+# ---- descriptors / site types (bit-exact) -------------------------------------------------------------------
+@pytest.mark.parametrize("d", [4, 7, 12, 16, 33])
+def test_descriptors_bit_exact(eng, d):
+    N = d * d
+    lat = eng.Lattice(d, "NH3")
+    x = np.vstack([Hp.random_structures(60, N, seed=100 + d), np.zeros((1, N), np.uint8), np.ones((1, N), np.uint8)])
+    ch = eng.Chains(lat, len(x))
+    ch.set_occupancy(x)
+    out = ch.descriptors(c6=True, lsc_type=True, nh3_type=True, lsc_hist=True, nh3_hist=True, nh3_exp=True)
+    assert (out["c6"] == ST.c6_counts(x, d)).all()
+    lsc = ST.lsc_types(x, d)
+    assert (out["lsc_type"] == lsc).all()
+    nh3 = ST.nh3_types(x, d)
+    assert (out["nh3_type"] == nh3).all()
+    assert (out["lsc_hist"] == np.stack([(lsc == t).sum(1) for t in range(3)], 1)).all()
+    assert (out["nh3_hist"] == ST.nh3_hist(nh3)).all()
+    assert (out["nh3_exp"] == ST.nh3_export_hist(nh3)).all()
+
+
+def test_descriptors_golden(eng):
+    z = np.load(os.path.join(Hp.GOLDEN, "types_golden.npz"))
+    for d in (6, 8):
+        x = z["x_d%d" % d]
+        ch = eng.Chains(eng.Lattice(d, "NH3"), len(x))
+        ch.set_occupancy(x)
+        out = ch.descriptors(lsc_type=True, nh3_type=True)
+        assert (out["lsc_type"] == z["lsc_d%d" % d]).all()
+        assert (out["nh3_type"] == z["nh3_d%d" % d]).all()
+
+
+@pytest.mark.parametrize("d", [4, 5, 12, 16])
+def test_flip_delta_bit_exact(eng, d):
+    N = d * d
+    n = 300
+    lat = eng.Lattice(d, "NH3")
+    x = Hp.random_structures(n, N, seed=7 + d)
+    sites = np.random.default_rng(d).integers(0, N, n).astype(np.int32)
+    ch = eng.Chains(lat, n)
+    ch.set_occupancy(x)
+    d_lsc, d_nh3 = ch.flip_delta(sites)
+    y = x.copy()
+    y[np.arange(n), sites] ^= 1
+    lsc0, lsc1 = ST.lsc_types(x, d), ST.lsc_types(y, d)
+    exp_lsc = np.stack([(lsc1 == t).sum(1) - (lsc0 == t).sum(1) for t in range(3)], 1)
+    e0, e1 = ST.nh3_export_hist(ST.nh3_types(x, d)), ST.nh3_export_hist(ST.nh3_types(y, d))
+    assert (d_lsc == exp_lsc).all()
+    assert (d_nh3 == e1 - e0).all()
+    assert (ch.get_occupancy() == x).all()                       # evaluation only, nothing applied
+
+
+# ---- surrogate scores -------------------------------------------------------------------------------------
+def _check_scores(eng, d, p, x):
+    lat = eng.Lattice(d, "LSC")
+    tab = Hp.tables_from_params(lat, p)
+    q = S.quantize(p)
+    assert (tab.e_h, tab.e_w, tab.Hp) == (q["e_h"], q["e_w"], q["Hp"])
+    ch = eng.Chains(lat, len(x))
+    ch.set_occupancy(x)
+    ch.attach(tab)
+    of, hi, lo, na = ch.objective(sums=True)
+    for c in range(len(x)):
+        o_of, o_hi, o_lo, o_n, _ = S.score_fixed(p, q, x[c], d)
+        assert (int(hi[c]), int(lo[c]), int(na[c])) == (o_hi, o_lo, o_n)       # exact integer sums
+        assert of[c] == o_of                                                   # pinned fp64 conversion
+        ref = S.eval_rate_fp64(p, L.descriptor_rows(x[c], p.offsets, d))
+        assert abs(of[c] - ref) <= 1e-5 * max(abs(ref), 1e-12) or (ref == 0 and of[c] == 0)
+    hq, _ = S.preact_fixed(p, q, x[0], d)
+    assert (ch.preact(0) == hq).all()
+    assert (ch.score() == of).all()                                            # recompute == tracked
+    rate, lh, ne = tab.score_batch(eng.pack_bits(x), want_lsc_hist=True)
+    assert (rate == of).all()
+    lsc = ST.lsc_types(x, d)
+    assert (lh == np.stack([(lsc == t).sum(1) for t in range(3)], 1)).all()
+    return ch, tab
+
+
+def test_scores_full_descriptor_gated(eng):
+    p = Hp.golden_surrogate(gated=True)
+    x = np.vstack([Hp.random_structures(40, 144, seed=11), np.zeros((1, 144), np.uint8), np.ones((1, 144), np.uint8)])
+    _check_scores(eng, 12, p, x)
+
+
+def test_scores_full_descriptor_open(eng):
+    _check_scores(eng, 12, Hp.golden_surrogate(gated=False), Hp.random_structures(40, 144, seed=12))
+
+
+@pytest.mark.parametrize("d,H", [(12, 20), (16, 20), (9, 7), (24, 32)])
+def test_scores_local_descriptor(eng, d, H):
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=H, seed=d, y_mean=0.3, y_scale=1.7)
+    _check_scores(eng, d, p, Hp.random_structures(24, d * d, seed=13 + d))
+
+
+def test_eval_rows(eng):
+    p = Hp.golden_surrogate(gated=True)
+    lat = eng.Lattice(12, "LSC")
+    tab = Hp.tables_from_params(lat, p)
+    X = (np.random.default_rng(0).random((500, 144)) < 0.6).astype(np.uint8)
+    active, rate = tab.eval_rows(X)
+    q = S.quantize(p)
+    assert (active == S.tree_predict(p.tree, X)).all()
+    ref = np.maximum(X @ p.W1 + p.b1, 0) @ p.w2 + p.b2
+    np.testing.assert_allclose(rate, ref * p.y_scale + p.y_mean, rtol=1e-5, atol=1e-7)
+
+
+# ---- annealing: decisions, occupancies, sums bit-exact against the fixed-point oracle --------------------------
+def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=False, exact_guard=False):
+    N = d * d
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    x0 = (rng.random((n_chains, N)) < 0.5).astype(np.uint8)
+    temps = SA.schedule("exp", T0, steps)
+    if use_philox:
+        prop, u = philox.draws(seed, np.arange(n_chains)[:, None] + 1000, np.arange(steps)[None, :] + 5, N)
+    else:
+        prop = rng.integers(0, N, size=(n_chains, steps)).astype(np.int32)
+        u = rng.random((n_chains, steps), dtype=np.float32)
+    lat = eng.Lattice(d, "LSC")
+    tab = Hp.tables_from_params(lat, p)
+    ch = eng.Chains(lat, n_chains)
+    ch.set_occupancy(x0)
+    ch.attach(tab)
+    if use_philox:
+        stats, acc = ch.anneal(temps, step0=5, seed=seed, chain_id0=1000, want_accept=True, variant=variant)
+    else:
+        stats, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True, variant=variant,
+                               exact_guard=exact_guard, guard_tol=1e-6)
+    q = S.quantize(p)
+    x1 = ch.get_occupancy()
+    of, hi, lo, na = ch.objective(sums=True)
+    n_acc = 0
+    for c in range(n_chains):
+        o = SA.anneal_fixed(p, q, d, x0[c], temps, prop[c], u[c])
+        if not exact_guard:
+            assert (acc[c].astype(bool) == o["accept"]).all(), "chain %d: accept/reject sequence differs" % c
+            assert (x1[c] == o["x"]).all()
+            assert (int(hi[c]), int(lo[c]), int(na[c])) == (o["hi"], o["lo"], o["n_act"])
+            assert of[c] == o["OF"]
+            if c == 0:
+                assert (ch.preact(0) == o["hq"]).all()
+        n_acc += int(acc[c].sum())
+    assert stats["accepted"] == n_acc and stats["flips"] == n_chains * steps
+    # state invariant: tracked state == fresh recompute from the final bits
+    tracked = ch.objective(sums=True)
+    fresh_of = ch.score()
+    again = ch.objective(sums=True)
+    assert (tracked[0] == fresh_of).all() and all((a == b).all() for a, b in zip(tracked, again))
+    return dict(x0=x0, x1=x1, acc=acc, prop=prop, u=u, temps=temps, of=of, stats=stats)
+
+
+def test_sa_flat_full_descriptor(eng):
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=False), n_chains=24, steps=1500, seed=21)
+
+
+def test_sa_flat_local_descriptor(eng):
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=3)
+    _run_sa(eng, 16, p, n_chains=40, steps=2000, seed=22)
+
+
+def test_sa_flat_local_small_lattice_wrap(eng):
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=4)
+    _run_sa(eng, 7, p, n_chains=16, steps=800, seed=23)          # 7x7 window on a 7x7 lattice: all wrap paths
+
+
+def test_sa_gated_full_descriptor(eng):
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24)
+
+
+def test_sa_row_kernel_equals_flat(eng):
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
+    a = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=0)
+    b = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=1)
+    assert (a["acc"] == b["acc"]).all() and (a["x1"] == b["x1"]).all() and (a["of"] == b["of"]).all()
+
+
+def test_sa_philox_draws(eng):
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=6)
+    _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=26, use_philox=True)
+
+
+def test_sa_odd_hidden_width(eng):
+    p = S.SurrogateParams.random_init(L.local_offsets(2), H=7, seed=7)
+    _run_sa(eng, 10, p, n_chains=8, steps=600, seed=27)
+
+
+def test_sa_quench_and_ties(eng):
+    """T == 0: accept iff delta > 0 (optimize_SA.py:113-116)."""
+    d, p = 12, Hp.golden_surrogate(gated=True)
+    rng = np.random.default_rng(9)
+    x0 = Hp.random_structures(6, 144, seed=9, coverage=0.5)
+    steps = 400
+    prop = rng.integers(0, 144, (6, steps)).astype(np.int32)
+    u = rng.random((6, steps), dtype=np.float32)
+    temps = SA.schedule("quench", 0.05, steps)
+    lat = eng.Lattice(d, "LSC")
+    ch = eng.Chains(lat, 6)
+    ch.set_occupancy(x0)
+    ch.attach(Hp.tables_from_params(lat, p))
+    of0 = ch.objective()
+    stats, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True)
+    q = S.quantize(p)
+    for c in range(6):
+        o = SA.anneal_fixed(p, q, d, x0[c], temps, prop[c], u[c])
+        assert (acc[c].astype(bool) == o["accept"]).all()
+    assert (ch.objective() >= of0).all()
+
+
+def test_sa_golden_vectors(eng):
+    """Committed oracle trajectories (faithful fp64 == fixed point) reproduced by the GPU."""
+    z = np.load(os.path.join(Hp.GOLDEN, "sa_d12_golden.npz"))
+    d = 12
+    for name, gated in (("gated", True), ("open", False)):
+        p = Hp.golden_surrogate(gated=gated)
+        lat = eng.Lattice(d, "LSC")
+        ch = eng.Chains(lat, len(z["x0"]))
+        ch.set_occupancy(z["x0"])
+        ch.attach(Hp.tables_from_params(lat, p))
+        stats, acc = ch.anneal(z["temps"], proposals=z["prop"], uniforms=z["u"], want_accept=True)
+        assert (acc.astype(bool) == z[name + "_fixed_accept"]).all()
+        assert (acc.astype(bool) == z[name + "_faithful_accept"]).all()
+        assert (ch.get_occupancy() == z[name + "_faithful_x"]).all()
+        of, hi, lo, _ = ch.objective(sums=True)
+        assert (hi == z[name + "_fixed_hi"]).all() and (lo == z[name + "_fixed_lo"]).all()
+        np.testing.assert_allclose(of, z[name + "_faithful_OF"], rtol=1e-5)
+
+
+def test_tscale_and_best(eng):
+    d = 12
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=8)
+    lat = eng.Lattice(d, "LSC")
+    ch = eng.Chains(lat, 50)
+    x = Hp.random_structures(50, 144, seed=30)
+    ch.set_occupancy(x)
+    ch.attach(Hp.tables_from_params(lat, p))
+    of = ch.objective()
+    best_of, best_chain, bits = ch.best()
+    assert best_chain == int(np.argmax(of)) and best_of == of.max()
+    assert (eng.unpack_bits(bits[None, :], 144)[0] == x[best_chain]).all()
+    ts = np.linspace(0.5, 2.0, 50)
+    ch.set_tscale(ts)
+    assert (ch.get_tscale() == ts).all()
+    # tscale scales the temperature: T = tscale * temps
+    steps = 300
+    rng = np.random.default_rng(2)
+    prop = rng.integers(0, 144, (50, steps)).astype(np.int32)
+    u = rng.random((50, steps), dtype=np.float32)
+    temps = SA.schedule("const", 0.05, steps)
+    stats, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True)
+    q = S.quantize(p)
+    for c in (0, 17, 49):
+        o = SA.anneal_fixed(p, q, d, x[c], temps, prop[c], u[c], tscale=ts[c])
+        assert (acc[c].astype(bool) == o["accept"]).all()
