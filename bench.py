@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark: SA flip-evaluations/sec (all chains, device-timed) on the 96x96 NiPt lattice.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun by the driver)
+  python bench.py --impl reference --steps K --warmup W    (the reference's CPU algorithm on the host cores)
+
+One "step" = one sweep (N = 9216 Metropolis steps) of every chain.  Workload (BASELINE.json configs[3]/[4]):
+d = 96, 65,536 chains per GPU, reference-width MLP 49 -> 20 -> 1 on the 7x7 local descriptor
+(OML/dynamic_cat.py:325-341), random-init weights (sklearn Glorot bounds), gate off, geometric ('exp') cooling
+from T_0 = 0.05, x0 ~ Bernoulli(0.5), Philox4x32-10 proposals/uniforms.  Chains shard across ranks with no
+data-path collective; at N > 1 a best-structure all-gather (NCCL) runs after every sweep inside the timed region,
+and --pt adds the parallel-tempering swap round of BASELINE configs[4] (fixed-temperature ladders strided across
+the GPUs, all-gather of the objectives + a deterministic swap kernel).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "structure-optimization_b200"))
+
+import numpy as np
+
+D, K_WIN, H, T0 = 96, 49, 20, 0.05
+METRIC = "SA flip-evaluations/sec (all chains, device-timed)"
+UNIT = "flip-evals/s"
+
+
+def glorot_mlp(offsets, hidden, seed):
+    """Random-init weights at the reference layer widths (sklearn's Glorot-uniform bounds)."""
+    rng = np.random.default_rng(seed)
+    k = len(offsets)
+    b = np.sqrt(6.0 / (k + hidden))
+    W1, b1 = rng.uniform(-b, b, (k, hidden)), rng.uniform(-b, b, hidden)
+    b = np.sqrt(6.0 / (hidden + 1))
+    return W1, b1, rng.uniform(-b, b, hidden), float(rng.uniform(-b, b))
+
+
+def exp_schedule(T_0, total_steps):
+    step = np.arange(total_steps, dtype=np.float64)
+    return T_0 * np.exp(-step / (total_steps / 5.0))          # OML/optimize_SA.py:26,64
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([v.strip() for v in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """The reference's algorithm (oracle port of OML/optimize_SA.py:59-132) on one chain: O(N*K) descriptor-matrix
+    copy + per-row update + full surrogate evaluation per step."""
+    seed, d, n_steps, total_steps, step0 = args
+    from oracle import lattice as L, surrogate as S, sa as SA, philox
+    offsets = L.local_offsets(3)
+    W1, b1, w2, b2 = glorot_mlp(offsets, H, 0)
+    p = S.SurrogateParams(offsets, W1, b1, w2, b2)
+
+    class Sur(object):
+        def eval_rate(self, M):
+            return S.eval_rate_fp64(p, M)
+    N = d * d
+    rng = np.random.default_rng(seed)
+    x0 = (rng.random(N) < 0.5).astype(np.uint8)
+    temps = exp_schedule(T0, total_steps)[step0:step0 + n_steps]
+    prop, u = philox.draws(seed, seed, np.arange(step0, step0 + n_steps), N)
+    t0 = time.perf_counter()
+    SA.optimize_faithful(x0, d, Sur(), offsets, temps, prop, u, n_record=1)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(d, flips_per_core, cores, total_steps):
+    """flip-evals/s of the reference CPU path with one independent chain per host core
+    (drivers/Online_learn_main.py:108-114 runs one structure per MPI rank)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, d, 2, total_steps, 0) for i in range(cores)])      # warm-up (imports, BLAS)
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i, d, flips_per_core, total_steps, 0) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    return cores * flips_per_core / wall, wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    d = a.d
+    total = (a.warmup + a.steps) * d * d
+    flips = a.ref_flips
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    per_step = []
+    with ctx.Pool(cores) as pool:
+        for s in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(i, d, flips, total, s * flips) for i in range(cores)])
+            per_step.append(time.perf_counter() - t0)
+    timed = per_step[a.warmup:]
+    value = cores * flips * len(timed) / sum(timed)
+    sample = "%d independent chains (one per core) x %d Metropolis steps per bench step, d=%d, K=49 local MLP" % (
+        cores, flips, d)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * sum(timed) / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, cores_note="reference CPU algorithm (oracle port), bounded sample"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(a, cores_note=None):
+    cfg = {"workload": "BASELINE configs[3]: %dx%d periodic NiPt lattice, %d chains per GPU, 49->20->1 MLP surrogate "
+                       "(7x7 local descriptor, random-init, gate off), exp cooling T0=%g" % (a.d, a.d, a.chains, T0),
+           "lattice": "%dx%d" % (a.d, a.d), "chains_per_gpu": a.chains, "descriptor": "local7x7", "hidden": H,
+           "step": "one sweep = %d Metropolis steps per chain" % (a.sweep_steps if a.sweep_steps > 0 else a.d * a.d),
+           "l2_policy": "working set (%.1f GB of per-chain state) >> 126 MB L2; no flush needed" % (
+               a.chains * a.d * a.d * H * 4 / 1e9),
+           "rng": "Philox4x32-10, key=seed, counter=(step, chain)"}
+    if cores_note:
+        cfg["note"] = cores_note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_gpu(a):
+    import torch
+    from so_b200 import engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    d = a.d
+    N = a.sweep_steps if a.sweep_steps > 0 else a.d * a.d          # Metropolis steps per chain per bench step
+    n_local = a.chains
+    lat = engine.Lattice(d, "NH3", device=local_rank)
+    offsets = engine.local_offsets(3)
+    W1, b1, w2, b2 = glorot_mlp(offsets, H, 0)
+    tab = engine.SurrogateTables(lat, offsets, W1, b1, w2, b2)
+    ch = engine.Chains(lat, n_local)
+    ch.randomize(seed=1234 + rank, coverage=0.5)
+    ch.attach(tab)
+
+    total_sweeps = a.warmup + a.steps
+    temps_all = exp_schedule(T0, total_sweeps * N)
+    chain_id0 = rank * n_local
+
+    from so_b200 import parallel
+    gather = parallel.BestGather(ch, chain_id0, world) if (world > 1 or a.pt) else None
+    pt = None
+    if a.pt:      # BASELINE configs[4]: fixed-temperature ladders (geometric in [T0*e^-5, T0]) + swap round per sweep
+        pt = parallel.ReplicaExchange(ch, ladder=a.ladder, seed=a.seed, rank=rank, world=world)
+        temps_all = np.full(total_sweeps * N, T0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def sweep(s):
+        st = ch.anneal(temps_all[s * N:(s + 1) * N], step0=s * N, seed=a.seed, chain_id0=chain_id0)
+        coll_ms = 0.0
+        if pt is not None or gather is not None:
+            ev0.record()
+            if pt is not None:
+                pt.round(s, t_ref=T0)
+            if gather is not None:
+                gather.gather()
+            ev1.record()
+            ev1.synchronize()
+            coll_ms = ev0.elapsed_time(ev1)
+        return st, coll_ms
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(a.warmup):
+        sweep(s)
+    barrier()
+    kern_ms, coll_ms, flips, accepted = 0.0, 0.0, 0, 0
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for s in range(a.warmup, total_sweeps):
+            st, cm = sweep(s)
+            kern_ms += st["kernel_ms"]
+            coll_ms += cm
+            flips += st["flips"]
+            accepted += st["accepted"]
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = kern_ms + coll_ms
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall_ms, float(flips), float(accepted)], dtype=torch.float64, device="cuda")
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms = float(mx[0]), float(mx[1])
+        flips_all, accepted_all = float(sm[2]), float(sm[3])
+    else:
+        flips_all, accepted_all = float(flips), float(accepted)
+    value = flips_all / (dev_ms * 1e-3)
+
+    # end-to-end through the public API with HOST buffers: H2D occupancy -> state build -> sweep -> D2H result
+    e2e = None
+    if a.e2e_steps > 0:
+        bits_host = ch.get_bits()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(a.e2e_steps):
+            ch.set_bits(bits_host)                                   # H2D + first-layer state rebuild
+            ch.anneal(temps_all[-N:], step0=(total_sweeps + s) * N, seed=a.seed, chain_id0=chain_id0)
+            bits_host = ch.get_bits()                                # D2H final occupancies
+            of = ch.objective()                                      # D2H objective per chain
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        e2e = {"value": world * n_local * N * a.e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(bits_host.nbytes + N * 8), "d2h_bytes_per_step": int(bits_host.nbytes + of.nbytes),
+               "steps": a.e2e_steps}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    acc_frac = accepted_all / max(flips_all, 1.0)
+    b_alg = 4.0 * K_WIN * H * (1.0 + acc_frac) + 15.0 + 4.0 * acc_frac       # SURVEY 8(d), bytes per flip-evaluation
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kern_s = kern_ms * 1e-3
+    achieved = (flips_all / world) * b_alg / kern_s / 1e9 if world == 1 else float(flips) * b_alg / kern_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("sa_flat_kernel")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed-point state / int64 sums / f64 Metropolis",
+        "data": "synthetic", "config": workload_config(a),
+        "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": a.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "sa_flat_kernel<5,8,true>",
+                     "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                     "launch_ms": kern_ms / a.steps},
+    }
+    if gather is not None:
+        line["collective_ms_per_step"] = coll_ms / a.steps
+        line["best_structure"] = {"of": gather.best[0], "chain": gather.best[1]}
+    if pt is not None:
+        line["config"]["parallel_tempering"] = {"ladder": a.ladder, "swaps_local_rank0": pt.swapped}
+    if world == 1 and a.cpu_flips > 0:
+        cores = os.cpu_count() or 1
+        v, wall = cpu_reference_rate(d, a.cpu_flips, cores, total_sweeps * N)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d chains (one per core) x %d Metropolis steps of the reference algorithm "
+                                          "(O(N*K) descriptor copy + full MLP evaluation per step), d=%d, %.1f s wall"
+                                          % (cores, a.cpu_flips, d, wall)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--d", type=int, default=D)
+    ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
+    ap.add_argument("--sweep-steps", type=int, default=0, help="Metropolis steps per chain per bench step (0 = d*d)")
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--pt", action="store_true", help="parallel tempering (BASELINE configs[4]): fixed ladders + swaps")
+    ap.add_argument("--ladder", type=int, default=8, help="parallel-tempering ladder size")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-flips", type=int, default=400, help="Metropolis steps per core for the CPU baseline (0 = skip)")
+    ap.add_argument("--ref-flips", type=int, default=100, help="Metropolis steps per core per bench step, --impl reference")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

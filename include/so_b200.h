@@ -157,13 +157,15 @@ int so_best(so_chains *c, double *of_out, int64_t *chain_out, uint32_t *bits);
 int so_best_record_dev(so_chains *c, int64_t chain_id0, void *record_dev, void *stream);
 /* tracked objectives of all local chains into DEVICE memory of_dev[n_chains] (fp64) on `stream`          */
 int so_objectives_dev(so_chains *c, double *of_dev, void *stream);
-/* parallel-tempering swap round over ladders of `ladder` consecutive GLOBAL chain ids.  of_all_dev and
- * tscale_all_dev are DEVICE arrays over all world*n_chains global chains (after an all-gather); every rank
- * takes the same decisions (Philox counter = (pair index, round)) and applies them to its own chains:
- * neighbours (r, r+1) with r = parity (mod 2) swap TEMPERATURES with probability
- * min(1, exp[(OF_r - OF_{r+1}) * (1/T_{r+1} - 1/T_r)]).  n_swapped counts swaps involving local chains.   */
-int so_exchange(so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, int parity, uint64_t seed,
-                int64_t round, double t_ref, const double *of_all_dev, double *tscale_all_dev, void *stream,
+/* parallel-tempering swap round.  Global chain g = i*world + rank (local chain i of `rank`: ladders of
+ * `ladder` consecutive global ids are strided across the ranks, so neighbouring rungs sit on different GPUs).
+ * of_all_dev / tscale_all_dev are DEVICE arrays in all-gather (rank-major) layout [world][n_chains]; every rank
+ * takes the same decisions (Philox counter = (ladder index, round, rung)) and applies them to its own chains:
+ * rungs ranked by current temperature, adjacent rungs (r, r+1), r = parity (mod 2), swap TEMPERATURES with
+ * probability min(1, exp[(OF_a - OF_b) * (1/T_b - 1/T_a)]), T = tscale * t_ref.  tscale_all_dev is updated in
+ * place (identically on every rank); n_swapped counts local chains whose temperature changed.           */
+int so_exchange(so_chains *c, int rank, int world, int ladder, int parity, uint64_t seed, int64_t round,
+                double t_ref, const double *of_all_dev, double *tscale_all_dev, void *stream,
                 int64_t *n_swapped);
 
 #ifdef __cplusplus

@@ -476,7 +476,26 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
     s->b1q_host[j] = (int32_t)nearbyint(ldexp(b1[j], -s->e_h));
     s->w2q_host[j] = (int32_t)nearbyint(ldexp(W2[j], -s->e_w));
   }
+  // rectangular-window descriptors get the pipelined kernel: rows in memory order p = p2*L + p1 <-> offset (b1-p1, b2-p2)
+  s->Wst_dev = nullptr;
+  std::vector<int32_t> Wst((size_t)K * Hp, 0);
+  {
+    int a1 = offsets[0], b1o = offsets[0], a2 = offsets[1], b2o = offsets[1];
+    for (int k = 0; k < K; ++k) {
+      a1 = std::min(a1, offsets[2 * k]); b1o = std::max(b1o, offsets[2 * k]);
+      a2 = std::min(a2, offsets[2 * k + 1]); b2o = std::max(b2o, offsets[2 * k + 1]);
+    }
+    int Lw = b1o - a1 + 1, nseg = b2o - a2 + 1;
+    s->win_ok = (Lw * nseg == K) && Lw <= d && nseg <= d && nseg <= 32;   // K distinct offsets in the box => full box
+    s->win_a1 = a1; s->win_b1 = b1o; s->win_a2 = a2; s->win_b2 = b2o;
+    if (s->win_ok)
+      for (int k = 0; k < K; ++k) {
+        int p = (b2o - offsets[2 * k + 1]) * Lw + (b1o - offsets[2 * k]);
+        memcpy(&Wst[(size_t)p * Hp], &s->W1q_host[(size_t)k * Hp], (size_t)Hp * 4);
+      }
+  }
   int rc = SO_OK;
+  if (rc == SO_OK) rc = upload(&s->Wst_dev, Wst.data(), (size_t)K * Hp);
   if (rc == SO_OK) rc = upload(&s->offs_dev, s->offs_host.data(), (size_t)K);
   if (rc == SO_OK) rc = upload(&s->W1q_dev, s->W1q_host.data(), (size_t)K * Hp);
   if (rc == SO_OK) rc = upload(&s->b1q_dev, s->b1q_host.data(), (size_t)Hp);
@@ -499,7 +518,7 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
 int so_surrogate_destroy(so_surrogate *s) {
   if (!s) return SO_OK;
   cudaSetDevice(s->device);
-  cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
+  cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
   cudaFree(s->W1d_dev); cudaFree(s->b1d_dev); cudaFree(s->w2d_dev);
   cudaFree(s->t_feature_dev); cudaFree(s->t_thr_dev); cudaFree(s->t_left_dev); cudaFree(s->t_right_dev);
   cudaFree(s->t_active_dev);
@@ -744,15 +763,17 @@ int so_objectives_dev(so_chains *c, double *of_dev, void *stream) {
   return so_launch_objective(c->sur, c->hi_dev, c->lo_dev, c->nact_dev, c->n_chains, of_dev, (cudaStream_t)stream);
 }
 
-int so_exchange(so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, int parity, uint64_t seed, int64_t round,
-                double t_ref, const double *of_all_dev, double *tscale_all_dev, void *stream, int64_t *n_swapped) {
+int so_exchange(so_chains *c, int rank, int world, int ladder, int parity, uint64_t seed, int64_t round, double t_ref,
+                const double *of_all_dev, double *tscale_all_dev, void *stream, int64_t *n_swapped) {
   SO_REQUIRE(c && of_all_dev && tscale_all_dev, "NULL argument");
   SO_REQUIRE(ladder >= 2 && ladder <= 32, "ladder size %d outside [2, 32]", ladder);
   SO_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
-  SO_REQUIRE(n_global % ladder == 0, "n_global=%lld is not a multiple of the ladder size %d", (long long)n_global, ladder);
-  SO_REQUIRE(chain_id0 >= 0 && chain_id0 + c->n_chains <= n_global, "local chains outside the global range");
+  SO_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
+  const int64_t n_global = c->n_chains * (int64_t)world;
+  SO_REQUIRE(n_global % ladder == 0, "world*n_chains=%lld is not a multiple of the ladder size %d", (long long)n_global,
+             ladder);
   SO_REQUIRE(t_ref > 0.0, "t_ref must be positive");
-  SO_CUDA(cudaSetDevice(c->lat->device));
+  SO_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (c->xch_cap < n_global) {
     cudaFree(c->xch_scratch);
@@ -762,7 +783,7 @@ int so_exchange(so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, i
     c->xch_cap = n_global;
   }
   SO_CUDA(cudaMemsetAsync(c->counters_dev + 4, 0, sizeof(unsigned long long), st));
-  SO_TRY(so_launch_exchange(c, chain_id0, n_global, ladder, parity, seed, round, t_ref, of_all_dev, tscale_all_dev,
+  SO_TRY(so_launch_exchange(c, rank, world, ladder, parity, seed, round, t_ref, of_all_dev, tscale_all_dev,
                             c->xch_scratch, c->counters_dev + 4, st));
   unsigned long long ns = 0;
   SO_CUDA(cudaMemcpyAsync(&ns, c->counters_dev + 4, sizeof(ns), cudaMemcpyDeviceToHost, st));

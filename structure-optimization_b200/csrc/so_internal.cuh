@@ -40,6 +40,8 @@ struct so_surrogate {
   double *t_thr_dev;
   uint8_t *t_active_dev;
   std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
+  int win_ok, win_a1, win_b1, win_a2, win_b2;   // descriptor offsets form the full rectangle [a1,b1] x [a2,b2]
+  int32_t *Wst_dev;                             // W1q rows in staged (memory) order of the window
 };
 
 struct so_chains {
@@ -89,7 +91,7 @@ struct SaParams {
   uint8_t *accept_out;
   int exact_guard;
   double guard_tol;
-  int variant;                          // 0 auto, 1 force the row-per-lane (gated) kernel
+  int variant;                          // 0 auto, 1 row-per-lane (gated) kernel, 2 generic flat kernel
   unsigned long long *counters;
   SurView sv;
 };
@@ -121,11 +123,13 @@ int so_launch_objective(const so_surrogate *s, const long long *hi, const long l
 int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_dev, uint8_t *active_dev,
                         double *rate_dev, cudaStream_t st);
 int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st);
+int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
+size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_apply_flips(const so_chains *c, int64_t n, const int64_t *chains_dev, const int32_t *sites_dev,
                           cudaStream_t st);
 int so_launch_best(const so_chains *c, int64_t chain_id0, void *record_dev, cudaStream_t st);
-int so_launch_exchange(const so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, int parity, uint64_t seed,
-                       int64_t round, double t_ref, const double *of_all, double *tscale_all, double *scratch,
+int so_launch_exchange(const so_chains *c, int rank, int world, int ladder, int parity, uint64_t seed, int64_t round,
+                       double t_ref, const double *of_all, double *tscale_all, double *scratch,
                        unsigned long long *n_swapped, cudaStream_t st);
 
 #ifdef __CUDACC__
@@ -173,4 +177,57 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SO_FULL, v); }
+
+// ---- tree gate ----------------------------------------------------------------------------------------
+// Descriptor column c of row (r1,r2) is the site (r1+o1[c], r2+o2[c]).
+__device__ __forceinline__ int tree_gate(const SurView &sv, const BitView &b, int r1, int r2) {
+  int node = 0;
+  int f = __ldg(sv.t_feature);
+  while (f >= 0) {
+    int off = __ldg(sv.offs + f);
+    int o1 = (int)(short)(off & 0xffff), o2 = off >> 16;
+    int bit = b.at(r1 + o1, r2 + o2);
+    node = ((double)bit <= __ldg(sv.t_thr + node)) ? __ldg(sv.t_left + node) : __ldg(sv.t_right + node);
+    f = __ldg(sv.t_feature + node);
+  }
+  return (int)__ldg(sv.t_active + node);
+}
+
+
+// Exact fp64 delta from the bits and the ORIGINAL fp64 weights, for near-tie decisions (whole warp).
+// Returns OF(x^e_f) - OF(x) as the difference of two window sums evaluated in the same lane order.
+__device__ inline double so_exact_delta(const SurView &sv, const uint32_t *bits, int d, int f, int lane) {
+  const int f2 = f / d, f1 = f - f2 * d;
+  BitView b0{bits, d, -1}, b1{bits, d, f};
+  double s_old = 0.0, s_new = 0.0;
+  for (int t = lane; t < sv.K; t += 32) {
+    int off = __ldg(sv.offs + t);
+    int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
+    double y0 = sv.b2, y1 = sv.b2;
+    for (int j = 0; j < sv.H; ++j) {
+      double h0 = __ldg(sv.b1d + j), h1 = h0;
+      for (int k = 0; k < sv.K; ++k) {
+        int o = __ldg(sv.offs + k);
+        int a1 = wrap(r1 + (int)(short)(o & 0xffff), d), a2 = wrap(r2 + (o >> 16), d);
+        double w = __ldg(sv.W1d + (long long)k * sv.H + j);
+        if (b0.site(a2 * d + a1)) h0 += w;
+        if (b1.site(a2 * d + a1)) h1 += w;
+      }
+      double w2 = __ldg(sv.w2d + j);
+      y0 += w2 * fmax(h0, 0.0);
+      y1 += w2 * fmax(h1, 0.0);
+    }
+    int g0 = sv.gated ? tree_gate(sv, b0, r1, r2) : 1;
+    int g1 = sv.gated ? tree_gate(sv, b1, r1, r2) : 1;
+    if (g0) s_old += y0 * sv.y_scale + sv.y_mean;
+    if (g1) s_new += y1 * sv.y_scale + sv.y_mean;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_old += __shfl_xor_sync(SO_FULL, s_old, o);
+    s_new += __shfl_xor_sync(SO_FULL, s_new, o);
+  }
+  return s_new - s_old;
+}
+
 #endif

@@ -11,21 +11,6 @@
 #include "so_internal.cuh"
 #include <math.h>
 
-// ---- tree gate ----------------------------------------------------------------------------------------
-// Descriptor column c of row (r1,r2) is the site (r1+o1[c], r2+o2[c]).
-__device__ __forceinline__ int tree_gate(const SurView &sv, const BitView &b, int r1, int r2) {
-  int node = 0;
-  int f = __ldg(sv.t_feature);
-  while (f >= 0) {
-    int off = __ldg(sv.offs + f);
-    int o1 = (int)(short)(off & 0xffff), o2 = off >> 16;
-    int bit = b.at(r1 + o1, r2 + o2);
-    node = ((double)bit <= __ldg(sv.t_thr + node)) ? __ldg(sv.t_left + node) : __ldg(sv.t_right + node);
-    f = __ldg(sv.t_feature + node);
-  }
-  return (int)__ldg(sv.t_active + node);
-}
-
 // ---- score: hq, row sums, gate, objective sums; one thread per row -------------------------------------
 template <int HP4>
 __global__ void __launch_bounds__(256) score_kernel(const uint32_t *__restrict__ bits, int d, int N, int W,
@@ -181,41 +166,6 @@ __device__ __forceinline__ bool metropolis(double delta, double T, float u, doub
   return acc;
 }
 
-// Exact fp64 delta from the bits and the ORIGINAL fp64 weights, for near-tie decisions (whole warp).
-// Returns OF(x^e_f) - OF(x) as the difference of two window sums evaluated in the same lane order.
-__device__ double exact_delta(const SurView &sv, const uint32_t *bits, int d, int f, int f1, int f2, int lane) {
-  BitView b0{bits, d, -1}, b1{bits, d, f};
-  double s_old = 0.0, s_new = 0.0;
-  for (int t = lane; t < sv.K; t += 32) {
-    int off = __ldg(sv.offs + t);
-    int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
-    double y0 = sv.b2, y1 = sv.b2;
-    for (int j = 0; j < sv.H; ++j) {
-      double h0 = __ldg(sv.b1d + j), h1 = h0;
-      for (int k = 0; k < sv.K; ++k) {
-        int o = __ldg(sv.offs + k);
-        int a1 = wrap(r1 + (int)(short)(o & 0xffff), d), a2 = wrap(r2 + (o >> 16), d);
-        double w = __ldg(sv.W1d + (long long)k * sv.H + j);
-        if (b0.site(a2 * d + a1)) h0 += w;
-        if (b1.site(a2 * d + a1)) h1 += w;
-      }
-      double w2 = __ldg(sv.w2d + j);
-      y0 += w2 * fmax(h0, 0.0);
-      y1 += w2 * fmax(h1, 0.0);
-    }
-    int g0 = sv.gated ? tree_gate(sv, b0, r1, r2) : 1;
-    int g1 = sv.gated ? tree_gate(sv, b1, r1, r2) : 1;
-    if (g0) s_old += y0 * sv.y_scale + sv.y_mean;
-    if (g1) s_new += y1 * sv.y_scale + sv.y_mean;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s_old += __shfl_xor_sync(SO_FULL, s_old, o);
-    s_new += __shfl_xor_sync(SO_FULL, s_new, o);
-  }
-  return s_new - s_old;
-}
-
 // ---- flat kernel: no gate.  One warp per chain; lane-strided over the K*HP4 int4 of the affected rows -----
 template <int HP4, int MAXIT, bool TAB_SMEM>
 __global__ void __launch_bounds__(256) sa_flat_kernel(SaParams P) {
@@ -295,7 +245,7 @@ __global__ void __launch_bounds__(256) sa_flat_kernel(SaParams P) {
       bool guard;
       bool accept = metropolis(delta, T, u, P.exact_guard ? P.guard_tol : 0.0, guard);
       if (guard) {
-        double de = exact_delta(sv, bits, d, f, f1, f2, lane);
+        double de = so_exact_delta(sv, bits, d, f, lane);
         bool g2;
         accept = metropolis(de, T, u, 0.0, g2);
         ++n_guard;
@@ -397,7 +347,7 @@ __global__ void __launch_bounds__(128) sa_gated_kernel(SaParams P) {
       bool guard;
       bool accept = metropolis(delta, T, u, P.exact_guard ? P.guard_tol : 0.0, guard);
       if (guard) {
-        double de = exact_delta(sv, s_bits, d, f, f1, f2, lane);
+        double de = so_exact_delta(sv, s_bits, d, f, lane);
         bool g2;
         accept = metropolis(de, T, u, 0.0, g2);
         ++n_guard;
@@ -494,23 +444,31 @@ __global__ void __launch_bounds__(1024) best_kernel(SurView sv, const long long 
 }
 
 // ---- replica exchange: one thread per temperature ladder (<= 32 rungs) -------------------------------------
-// Chains of a ladder are ranked by their current temperature (hottest first, ties by chain id); adjacent
+// Global chain g = i*world + rank lives at position (g % world)*n_local + g/world of the all-gathered arrays.
+// Chains of a ladder are ranked by their current temperature (hottest first, ties by global id); adjacent
 // rungs (r, r+1), r = parity (mod 2), swap TEMPERATURES with probability
 // min(1, exp[(OF_a - OF_b) * (1/T_b - 1/T_a)]) (maximisation, pi ~ exp(OF/T)).
-__global__ void exchange_kernel(long long n_global, int ladder, int parity, unsigned long long seed, long long round,
-                                double t_ref, const double *of_all, const double *tscale_all, double *tscale_new) {
+__global__ void exchange_kernel(long long n_local, int world, int ladder, int parity, unsigned long long seed,
+                                long long round, double t_ref, const double *of_all, const double *tscale_all,
+                                double *tscale_new) {
   long long lad = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long n_global = n_local * world;
   if (lad >= n_global / ladder) return;
   long long base = lad * ladder;
+  long long pos[32];
   int order[32];
+  for (int i = 0; i < ladder; ++i) {
+    long long g = base + i;
+    pos[i] = (g % world) * n_local + g / world;
+  }
   for (int i = 0; i < ladder; ++i) {   // insertion sort, descending temperature, stable
     int j = i;
-    double ti = tscale_all[base + i];
-    while (j > 0 && tscale_all[base + order[j - 1]] < ti) { order[j] = order[j - 1]; --j; }
+    double ti = tscale_all[pos[i]];
+    while (j > 0 && tscale_all[pos[order[j - 1]]] < ti) { order[j] = order[j - 1]; --j; }
     order[j] = i;
   }
   for (int r = parity; r + 1 < ladder; r += 2) {
-    long long a = base + order[r], b = base + order[r + 1];
+    long long a = pos[order[r]], b = pos[order[r + 1]];
     double Ta = tscale_all[a] * t_ref, Tb = tscale_all[b] * t_ref;
     double arg = (of_all[a] - of_all[b]) * (1.0 / Tb - 1.0 / Ta);
     uint32_t o[4];
@@ -525,15 +483,15 @@ __global__ void exchange_kernel(long long n_global, int ladder, int parity, unsi
   }
 }
 
-__global__ void exchange_commit_kernel(long long n_global, long long chain_id0, long long n_local, double *tscale_all,
+__global__ void exchange_commit_kernel(long long n_global, long long pos0, long long n_local, double *tscale_all,
                                        const double *tscale_new, double *tscale_local, unsigned long long *n_swapped) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n_global) return;
   double v = tscale_new[t];
   bool changed = v != tscale_all[t];
   tscale_all[t] = v;
-  if (t >= chain_id0 && t < chain_id0 + n_local) {
-    tscale_local[t - chain_id0] = v;
+  if (t >= pos0 && t < pos0 + n_local) {
+    tscale_local[t - pos0] = v;
     if (changed) atomicAdd(n_swapped, 1ULL);
   }
 }
@@ -617,6 +575,10 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
   int dev = c->lat->device, n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
+  if (!s->gated && P.variant == 0 && s->win_ok && s->K * s->HP4 <= 256 &&
+      so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 112 * 1024) {
+    return so_launch_anneal_window(c, P, st);
+  }
   if (!s->gated && P.variant != 1) {
     int Q = s->K * s->HP4;
     size_t tab = (size_t)Q * 16 + (size_t)s->K * 4;
@@ -662,19 +624,19 @@ int so_launch_best(const so_chains *c, int64_t chain_id0, void *record_dev, cuda
   return SO_OK;
 }
 
-int so_launch_exchange(const so_chains *c, int64_t chain_id0, int64_t n_global, int ladder, int parity, uint64_t seed,
-                       int64_t round, double t_ref, const double *of_all, double *tscale_all, double *scratch,
+int so_launch_exchange(const so_chains *c, int rank, int world, int ladder, int parity, uint64_t seed, int64_t round,
+                       double t_ref, const double *of_all, double *tscale_all, double *scratch,
                        unsigned long long *n_swapped, cudaStream_t st) {
+  long long n_global = c->n_chains * (long long)world;
   SO_CUDA(cudaMemcpyAsync(scratch, tscale_all, n_global * sizeof(double), cudaMemcpyDeviceToDevice, st));
   long long ladders = n_global / ladder;
   if (ladders > 0) {
-    exchange_kernel<<<(unsigned)((ladders + 127) / 128), 128, 0, st>>>(n_global, ladder, parity, seed, round, t_ref,
-                                                                       of_all, tscale_all, scratch);
+    exchange_kernel<<<(unsigned)((ladders + 127) / 128), 128, 0, st>>>(c->n_chains, world, ladder, parity, seed, round,
+                                                                       t_ref, of_all, tscale_all, scratch);
     SO_CUDA(cudaGetLastError());
   }
-  exchange_commit_kernel<<<(unsigned)((n_global + 255) / 256), 256, 0, st>>>(n_global, chain_id0, c->n_chains,
-                                                                             tscale_all, scratch, c->tscale_dev,
-                                                                             n_swapped);
+  exchange_commit_kernel<<<(unsigned)((n_global + 255) / 256), 256, 0, st>>>(
+      n_global, (long long)rank * c->n_chains, c->n_chains, tscale_all, scratch, c->tscale_dev, n_swapped);
   SO_CUDA(cudaGetLastError());
   return SO_OK;
 }

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "so_best": (C.c_int, [C.c_void_p, c_f64p, c_i64p, c_u32p]),
     "so_best_record_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "so_objectives_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "so_exchange": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_double,
+    "so_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
 }
 
