@@ -191,7 +191,8 @@ def test_eval_rows(eng):
 
 
 # ---- annealing: decisions, occupancies, sums bit-exact against the fixed-point oracle --------------------------
-def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=False, exact_guard=False):
+def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=False, exact_guard=False,
+            check_chains=None):
     N = d * d
     rng = np.random.Generator(np.random.Philox(key=seed))
     x0 = (rng.random((n_chains, N)) < 0.5).astype(np.uint8)
@@ -214,8 +215,8 @@ def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=Fal
     q = S.quantize(p)
     x1 = ch.get_occupancy()
     of, hi, lo, na = ch.objective(sums=True)
-    n_acc = 0
-    for c in range(n_chains):
+    n_acc = int(acc.sum())
+    for c in (range(n_chains) if check_chains is None else check_chains):
         o = SA.anneal_fixed(p, q, d, x0[c], temps, prop[c], u[c])
         if not exact_guard:
             assert (acc[c].astype(bool) == o["accept"]).all(), "chain %d: accept/reject sequence differs" % c
@@ -224,7 +225,6 @@ def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=Fal
             assert of[c] == o["OF"]
             if c == 0:
                 assert (ch.preact(0) == o["hq"]).all()
-        n_acc += int(acc[c].sum())
     assert stats["accepted"] == n_acc and stats["flips"] == n_chains * steps
     # state invariant: tracked state == fresh recompute from the final bits
     tracked = ch.objective(sums=True)
@@ -243,20 +243,41 @@ def test_sa_flat_local_descriptor(eng):
     _run_sa(eng, 16, p, n_chains=40, steps=2000, seed=22)
 
 
-def test_sa_flat_local_small_lattice_wrap(eng):
+@pytest.mark.parametrize("T0", [0.05, 2.0])
+def test_sa_flat_local_small_lattice_wrap(eng, T0):
+    """7x7 window on a 7x7 lattice: every wrap path, and (hot run: most flips accepted) every prefetched window is
+    stale -- the hazard paths of the pipelined kernel."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=4)
-    _run_sa(eng, 7, p, n_chains=16, steps=800, seed=23)          # 7x7 window on a 7x7 lattice: all wrap paths
+    r = _run_sa(eng, 7, p, n_chains=16, steps=800, seed=23, T0=T0)
+    if T0 > 1:
+        assert r["acc"].mean() > 0.5
+
+
+@pytest.mark.parametrize("d", [8, 12, 20])
+def test_sa_window_hot_chains(eng, d):
+    """High acceptance on small lattices: overlapping windows of consecutive flips are the common case."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=40 + d)
+    r = _run_sa(eng, d, p, n_chains=32, steps=1500, seed=50 + d, T0=1.0)
+    assert r["acc"].mean() > 0.3
+
+
+def test_sa_window_many_chains(eng):
+    """More chains than resident warps: dynamic chain hand-out + stage/mbarrier reuse across chains."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=41)
+    _run_sa(eng, 12, p, n_chains=5000, steps=70, seed=51, T0=0.5, check_chains=range(0, 5000, 97))
 
 
 def test_sa_gated_full_descriptor(eng):
     _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24)
 
 
-def test_sa_row_kernel_equals_flat(eng):
+def test_sa_kernel_variants_agree(eng):
+    """window (pipelined) == generic flat == row-per-lane kernels, bit for bit."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
-    a = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=0)
-    b = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=1)
-    assert (a["acc"] == b["acc"]).all() and (a["x1"] == b["x1"]).all() and (a["of"] == b["of"]).all()
+    a = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=0, T0=0.3)
+    for variant in (1, 2):
+        b = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=variant, T0=0.3)
+        assert (a["acc"] == b["acc"]).all() and (a["x1"] == b["x1"]).all() and (a["of"] == b["of"]).all()
 
 
 def test_sa_philox_draws(eng):
