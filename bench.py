@@ -286,7 +286,7 @@ def run_gpu(a):
     tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("sa_flat_kernel")
+            traffic = json.load(open(tpath)).get("sa_window_kernel")
         except Exception:
             traffic = None
     line = {
@@ -296,7 +296,7 @@ def run_gpu(a):
         "data": "synthetic", "config": workload_config(a),
         "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sa_flat_kernel<5,8,true>",
+                     "traffic": traffic, "kernel": "sa_window_kernel<5,3>",
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "launch_ms": kern_ms / a.steps},
     }

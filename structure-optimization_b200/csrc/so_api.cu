@@ -557,6 +557,30 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
     return SO_ENOMEM;
   }
   c->sur = s;
+  // tensor map over hq viewed as int32 [n_chains][d][d*Hp]; one box = the window of a flip (so_sa_window.cu)
+  c->tmap_ok = 0;
+  if (s->win_ok && !s->gated) {
+    const int Lw = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
+    if ((uint64_t)Lw * s->Hp <= 256 && nseg <= 256) {
+      typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+          qres == cudaDriverEntryPointSuccess) {
+        cuuint64_t gdim[3] = {(cuuint64_t)L->d * s->Hp, (cuuint64_t)L->d, (cuuint64_t)c->n_chains};
+        cuuint64_t gstr[2] = {(cuuint64_t)L->d * s->Hp * 4, (cuuint64_t)L->N * s->Hp * 4};
+        cuuint32_t box[3] = {(cuuint32_t)(Lw * s->Hp), (cuuint32_t)nseg, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult cr = ((EncodeFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, c->hq_dev, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_ok = (cr == CUDA_SUCCESS) ? 1 : 0;
+      }
+      (void)cudaGetLastError();
+    }
+  }
   SO_TRY(rescore(c, 0, c->n_chains));
   SO_CUDA(cudaStreamSynchronize(c->stream));
   return SO_OK;

@@ -1,5 +1,6 @@
 // so_internal.cuh -- shared declarations of the sm_100a hot path (not part of the public C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -59,6 +60,8 @@ struct so_chains {
   int64_t xch_cap;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
+  CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
+  int tmap_ok;
 };
 
 // ---- device-side views ------------------------------------------------------------------------------

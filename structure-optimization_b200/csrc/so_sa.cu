@@ -576,7 +576,7 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
   if (!s->gated && P.variant == 0 && s->win_ok && s->K * s->HP4 <= 256 &&
-      so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 112 * 1024) {
+      so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 113 * 1024) {
     return so_launch_anneal_window(c, P, st);
   }
   if (!s->gated && P.variant != 1) {

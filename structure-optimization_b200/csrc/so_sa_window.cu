@@ -12,6 +12,7 @@
 //     store still in flight) are detected exactly and resolved by draining the stores and re-fetching;
 //   * Philox and the injected-sequence loads are evaluated lane-parallel for 32 steps at a time; the warp sum uses
 //     three REDUX.SUM on 21-bit limbs; exp() runs in fp64 only when an fp32 pre-filter cannot decide.
+#include <cuda.h>
 #include "so_internal.cuh"
 #include <math.h>
 
@@ -50,54 +51,186 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 struct WinGeom {
   int b1, b2;        // largest offsets: window row p2 / column p1 <-> site (f1 - b1 + p1, f2 - b2 + p2)
   int L, n_seg;      // sites per segment, number of segments
+  int use_tma;       // interior windows go through one tensor-TMA box
+  int stage_i4;      // int4 per shared-memory stage: window + zero-weight padding, multiple of 8 (128 B)
+  int nslots;        // lane slots per window: ceil(Q / STRIDE)
 };
 
-// cyclic |a - b| <= r
-__device__ __forceinline__ bool near_cyclic(int a, int b, int r, int d) {
-  int t = a - b;
-  t = t < 0 ? -t : t;
-  t = min(t, d - t);
-  return t <= r;
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// packed site coordinates: f1 | f2 << 16
+__device__ __forceinline__ int pk1(int p) { return p & 0xffff; }
+__device__ __forceinline__ int pk2(int p) { return p >> 16; }
+__device__ __forceinline__ bool near_cyclic(int a, int b, int r, int d) {   // cyclic |a - b| <= r
+  int t = abs(a - b);
+  return min(t, d - t) <= r;
 }
 
 constexpr int WARPS = 8;
 
-template <int HP4, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 2) sa_window_kernel(SaParams P, WinGeom g, const int4 *__restrict__ Wst) {
-  constexpr int MAXIT = 8;
+// ---- cold paths, kept out of line so that they do not cost the hot loop registers ---------------------------------
+// lane-parallel draws of steps 32b .. 32b+31: packed site (f1 | f2 << 16), uniform, temperature.  Everything is
+// passed and returned BY VALUE: an address-taken argument would pin the caller's variables in local memory.
+struct Draw {
+  int f;
+  float u;
+  double t;
+};
+__device__ __noinline__ Draw draw_batch_cold(const double *temps, const int32_t *proposals, const float *uniforms,
+                                             long long n_steps, long long step0, long long chain_id, long long c,
+                                             unsigned long long seed, int N, int d, long long b, int lane) {
+  long long s = b * 32 + lane;
+  Draw r;
+  int f = 0;
+  r.u = 0.f;
+  r.t = 0.0;
+  if (s < n_steps) {
+    r.t = __ldg(temps + s);
+    if (proposals) {
+      f = __ldg(proposals + c * n_steps + s);
+      r.u = __ldg(uniforms + c * n_steps + s);
+    } else {
+      unsigned long long step = (unsigned long long)(step0 + s), cid = (unsigned long long)chain_id;
+      uint32_t o[4];
+      philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)seed,
+                    (uint32_t)(seed >> 32), o);
+      f = (int)__umulhi(o[0], (uint32_t)N);
+      r.u = (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+    }
+  }
+  int f2 = f / d;
+  r.f = (f - f2 * d) | (f2 << 16);
+  return r;
+}
+
+// the fp64 Metropolis rule (OML/optimize_SA.py:108-116) + the near-tie guard; bit 0 = accept, bit 1 = guard
+__device__ __noinline__ int metropolis_cold(double delta, double T, float u, int exact_guard, double tol) {
+  bool accept, guard = false;
+  if (delta > 0.0) {
+    accept = true;
+    if (exact_guard && T <= 0.0 && delta < tol) guard = true;
+  } else if (T > 0.0) {
+    accept = exp(delta / T) > (double)u;
+    if (exact_guard && u > 0.f) guard = fabs(delta - T * log((double)u)) < tol;
+  } else {
+    accept = false;
+    if (exact_guard && delta > -tol) guard = true;
+  }
+  return (accept ? 1 : 0) | (guard ? 2 : 0);
+}
+
+__device__ __noinline__ int exact_decision_cold(const SurView sv, const uint32_t *bits, int d, int f, int lane, double T,
+                                                float u) {
+  double de = so_exact_delta(sv, bits, d, f, lane);
+  if (de > 0.0) return 1;
+  if (T > 0.0) return exp(de / T) > (double)u ? 1 : 0;
+  return 0;
+}
+
+// windows that cross the periodic boundary (about 2*(L+n_seg)/d of all flips): n_seg (x2) plain bulk copies, lane 0
+__device__ __noinline__ void boundary_loads_cold(const int4 *hq, uint32_t dst, uint32_t bar, int f1, int f2, int b1,
+                                                 int b2, int L, int n_seg, int d, int hp4) {
+  const uint32_t site_bytes = hp4 * 16;
+  int start = f1 - b1;
+  if (start < 0) start += d;
+  const int n1 = min(L, d - start);
+  for (int sg = 0; sg < n_seg; ++sg) {
+    const int4 *row = hq + (size_t)wrap(f2 - b2 + sg, d) * d * hp4;
+    const uint32_t dseg = dst + (uint32_t)(sg * L) * site_bytes;
+    bulk_load(dseg, row + (size_t)start * hp4, (uint32_t)n1 * site_bytes, bar);
+    if (n1 < L) bulk_load(dseg + (uint32_t)n1 * site_bytes, row, (uint32_t)(L - n1) * site_bytes, bar);
+  }
+}
+__device__ __noinline__ void boundary_stores_cold(int4 *hq, uint32_t src, int f1, int f2, int b1, int b2, int L, int n_seg,
+                                                  int d, int hp4) {
+  const uint32_t site_bytes = hp4 * 16;
+  int start = f1 - b1;
+  if (start < 0) start += d;
+  const int n1 = min(L, d - start);
+  for (int sg = 0; sg < n_seg; ++sg) {
+    int4 *row = hq + (size_t)wrap(f2 - b2 + sg, d) * d * hp4;
+    const uint32_t sseg = src + (uint32_t)(sg * L) * site_bytes;
+    bulk_store(row + (size_t)start * hp4, sseg, (uint32_t)n1 * site_bytes);
+    if (n1 < L) bulk_store(row, sseg + (uint32_t)n1 * site_bytes, (uint32_t)(L - n1) * site_bytes);
+  }
+}
+// a prefetched window went stale (a flip accepted after its prefetch overlaps it): all lanes re-read it from L2
+// with plain loads once the pending stores have drained
+__device__ __noinline__ void reload_window_cold(int4 *stage, const int4 *hq, int f1, int f2, int b1, int b2, int L, int Q,
+                                                int d, int hp4, int lane) {
+  for (int q = lane; q < Q; q += 32) {
+    int p = q / hp4, part = q - p * hp4;
+    int p2 = p / L, p1 = p - p2 * L;
+    int r1 = wrap(f1 - b1 + p1, d), r2 = wrap(f2 - b2 + p2, d);
+    stage[q] = __ldcg(hq + ((size_t)r2 * d + r1) * hp4 + part);
+  }
+}
+
+// slow, exact side of the Metropolis rule for one step; reloads the fp64 temperature.  bit 0 accept, bit 1 guard
+__device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_c, double tsc, const double *temps,
+                                        long long s, float u, int exact_guard, double tol) {
+  // == so_real(c, b2, sigma, mu, acc >> 20, acc & mask, 0): with n = 0 the pinned sequence reduces to
+  // sigma * (c * RN(acc)) (the dropped terms add +0.0; |acc| < 2^62 so hi*2^20 + lo rounds once, like the cast)
+  const double delta = __dmul_rn(k_sigma, __dmul_rn(k_c, __ll2double_rn(acc)));
+  const double T = __dmul_rn(tsc, __ldg(temps + s));
+  return metropolis_cold(delta, T, u, exact_guard, tol);
+}
+
+template <int HP4, int NSLOTS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+    sa_window_kernel(SaParams P, WinGeom g, const int4 *__restrict__ Wst, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int STAGES = 3;
+  // lanes 0..STRIDE-1 own int4 slots q = lane + STRIDE*it, it < NSLOTS; STRIDE is a multiple of HP4, so a lane always
+  // sees the same hidden-unit quad and its four second-layer weights live in registers
+  constexpr int STRIDE = (32 / HP4) * HP4;
   extern __shared__ __align__(128) unsigned char s_raw[];
-  const SurView &sv = P.sv;
-  const int Q = sv.K * HP4;                       // int4 per window
+  const int Q = P.sv.K * HP4;                     // int4 per window
+  const int stage_i4 = g.stage_i4;                // window + zero-weight padding, multiple of 8 int4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d;
-  // shared layout: [w2: HP4 int4][per warp: STAGES stages of Q int4][per warp: bits W u32][per warp: STAGES mbarriers]
-  int4 *s_w2 = (int4 *)s_raw;
-  const int stage_i4 = Q;                                                     // int4 per stage
-  int4 *s_stage = s_w2 + 8 + (size_t)warp * STAGES * stage_i4;                // 8 int4 reserved for w2
-  uint32_t *s_bits = (uint32_t *)(s_w2 + 8 + (size_t)WARPS * STAGES * stage_i4) + (size_t)warp * P.W;
+  // shared layout: [per warp: STAGES stages][+W: stage_i4][-W: stage_i4][w2: 8 int4][per warp: bits][per warp: mbarriers]
+  int4 *s_stage = (int4 *)s_raw + (size_t)warp * STAGES * stage_i4;
+  int4 *s_Wp = (int4 *)s_raw + (size_t)WARPS * STAGES * stage_i4;
+  int4 *s_Wn = s_Wp + stage_i4;
+  int4 *s_w2 = s_Wn + stage_i4;
+  uint32_t *s_bits = (uint32_t *)(s_w2 + 8) + (size_t)warp * P.W;
   unsigned long long *s_bar =
-      (unsigned long long *)((uint32_t *)(s_w2 + 8 + (size_t)WARPS * STAGES * stage_i4) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) +
-      warp * STAGES;
-  if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)sv.w2q)[threadIdx.x];
+      (unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) + warp * STAGES;
+  if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
+  // (entries beyond the window are zero: the clamped last slot and the padding contribute exactly 0)
+  for (int q = threadIdx.x; q < stage_i4; q += blockDim.x) {
+    int4 w = q < Q ? Wst[q] : make_int4(0, 0, 0, 0);
+    s_Wp[q] = w;
+    s_Wn[q] = make_int4(-w.x, -w.y, -w.z, -w.w);
+  }
   if (lane == 0)
     for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(s_bar + i), 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_async_smem();
   __syncthreads();
 
-  // lane-constant tables: this lane's int4 slots q = lane + 32*it of the window, their weights
-  int4 Wreg[MAXIT];
-  int part[MAXIT];
-#pragma unroll
-  for (int it = 0; it < MAXIT; ++it) {
-    int q = lane + 32 * it;
-    Wreg[it] = q < Q ? Wst[q] : make_int4(0, 0, 0, 0);
-    part[it] = q < Q ? q % HP4 : 0;
-  }
-  const uint32_t seg_bytes_site = HP4 * 16;
-  const uint32_t stage_bytes = (uint32_t)Q * 16;
+  const int4 w2 = lane < STRIDE ? s_w2[lane % HP4] : make_int4(0, 0, 0, 0);   // idle lanes re-read data with weight 0
+  // every slot but the last stays inside the padded stage; the last one is clamped onto a zero-weight padding entry
+  const int last_off = min(lane + STRIDE * (NSLOTS - 1), stage_i4 - 1) - lane;
+  const uint32_t stage_bytes = (uint32_t)Q * 16, stage_pitch = (uint32_t)stage_i4 * 16;
+  const uint32_t stage0 = smem_u32(s_stage), bar0 = smem_u32(s_bar);
   uint32_t phase_bits = 0;                          // parity of each stage's mbarrier (bit i)
-  const double k_c = sv.c, k_sigma = sv.y_scale;
+  const float k_f = (float)(P.sv.y_scale * P.sv.c);
+  const bool sigma_pos = P.sv.y_scale > 0.0;
+  const int gb1 = g.b1, gb2 = g.b2, gL = g.L, gseg = g.n_seg;
+  const bool use_tma = g.use_tma != 0;
+  const bool fast_ok = !P.exact_guard;
 
   for (;;) {
     long long c = 0;
@@ -109,199 +242,153 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sa_window_kernel(SaParams P, Wi
     int4 *hq = (int4 *)P.hq + c * (long long)P.N * HP4;
     long long hi = P.hi[c], lo = P.lo[c];
     const double tsc = P.tscale[c];
+    const float tsc_f = (float)tsc;
     unsigned n_acc = 0, n_guard = 0;
     __syncwarp();
 
-    // lane-parallel draws for 32 steps at a time: batch b covers steps 32b .. 32b+31
-    int f_cur = 0, f_nxt = 0;
-    float u_cur = 0.f, u_nxt = 0.f;
-    auto draw_batch = [&](long long b, int &fo, float &uo) {
-      long long s = b * 32 + lane;
-      fo = 0; uo = 0.f;
-      if (s < P.n_steps) {
-        if (P.proposals) {
-          fo = __ldg(P.proposals + c * P.n_steps + s);
-          uo = __ldg(P.uniforms + c * P.n_steps + s);
-        } else {
-          unsigned long long step = (unsigned long long)(P.step0 + s), cid = (unsigned long long)(P.chain_id0 + c);
-          uint32_t o[4];
-          philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)P.seed,
-                        (uint32_t)(P.seed >> 32), o);
-          fo = (int)__umulhi(o[0], (uint32_t)P.N);
-          uo = (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+    Draw batch;                                     // lane l: draws of step 32*b + l
+    batch.f = 0; batch.u = 0.f; batch.t = 0.0;
+    float batch_tf = 0.f;
+    // pipeline registers: draws of the steps whose windows are in flight
+    int f_a = 0, f_b = 0;
+    float u_a = 0.f, u_b = 0.f, t_a = 0.f, t_b = 0.f;
+    int hist0 = -1, hist1 = -1, pend_f = -1;        // flips accepted at steps s-1, s-2; flip whose stores may be in flight
+    int slot = 1;                                   // stage of step s (s starts at -(STAGES-1) = -2)
+
+    for (long long s = -(STAGES - 1); s < P.n_steps; ++s) {
+      // ---- 1. prefetch the window of step s+2 into the stage freed by step s-1 -------------------------------
+      const long long sp = s + (STAGES - 1);
+      int f_q = 0;
+      float u_q = 0.f, t_q = 0.f;
+      if (sp < P.n_steps) {
+        if ((sp & 31) == 0) {
+          batch = draw_batch_cold(P.temps, P.proposals, P.uniforms, P.n_steps, P.step0, P.chain_id0 + c, c, P.seed, P.N, d,
+                                  sp >> 5, lane);
+          batch_tf = (float)batch.t;
+        }
+        f_q = __shfl_sync(SO_FULL, batch.f, (int)(sp & 31));
+        u_q = __shfl_sync(SO_FULL, batch.u, (int)(sp & 31));
+        t_q = __shfl_sync(SO_FULL, batch_tf, (int)(sp & 31));
+        const int pslot = slot == 0 ? STAGES - 1 : slot - 1;
+        const int q1 = pk1(f_q), q2 = pk2(f_q);
+        if (pend_f >= 0 && near_cyclic(q1, pk1(pend_f), gL - 1, d) && near_cyclic(q2, pk2(pend_f), gseg - 1, d)) {
+          bulk_wait_all();                          // the store of that region may still be in flight
+          pend_f = -1;
+          __syncwarp();
+        }
+        if (lane == 0) {
+          const uint32_t bar = bar0 + pslot * 8, dst = stage0 + pslot * stage_pitch;
+          mbar_expect_tx(bar, stage_bytes);
+          if (use_tma && q1 - gb1 >= 0 && q1 - gb1 + gL <= d && q2 - gb2 >= 0 && q2 - gb2 + gseg <= d)
+            tma_load_3d(dst, &tmap, (q1 - gb1) * (HP4 * 4), q2 - gb2, (int)c, bar);
+          else
+            boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, HP4);
         }
       }
-    };
-    draw_batch(0, f_cur, u_cur);
-    draw_batch(1, f_nxt, u_nxt);
-    // issue the bulk loads of the window around site f into stage `slot`
-    auto issue_loads = [&](int f, int slot) {
-      const int f2 = f / d, f1 = f - f2 * d;
-      const uint32_t bar = smem_u32(s_bar + slot);
-      if (lane == 0) mbar_expect_tx(bar, stage_bytes);
-      __syncwarp();
-      if (lane < g.n_seg) {
-        const int r2 = wrap(f2 - g.b2 + lane, d);
-        int start = f1 - g.b1;                                       // first site of the segment, may be < 0
-        const uint32_t dst = smem_u32(s_stage + (size_t)slot * stage_i4 + (size_t)lane * g.L * HP4);
-        const int4 *row = hq + (size_t)r2 * d * HP4;
-        int n1;                                                      // sites before the wrap point
-        if (start < 0) { start += d; n1 = min(g.L, d - start); }
-        else n1 = min(g.L, d - start);
-        bulk_load(dst, row + (size_t)start * HP4, (uint32_t)n1 * seg_bytes_site, bar);
-        if (n1 < g.L) bulk_load(dst + (uint32_t)n1 * seg_bytes_site, row, (uint32_t)(g.L - n1) * seg_bytes_site, bar);
-      }
-    };
-    // write the (updated) window in stage `slot` back to global memory
-    auto issue_stores = [&](int f, int slot) {
-      const int f2 = f / d, f1 = f - f2 * d;
-      if (lane < g.n_seg) {
-        const int r2 = wrap(f2 - g.b2 + lane, d);
-        int start = f1 - g.b1;
-        const uint32_t src = smem_u32(s_stage + (size_t)slot * stage_i4 + (size_t)lane * g.L * HP4);
-        int4 *row = hq + (size_t)r2 * d * HP4;
-        if (start < 0) start += d;
-        int n1 = min(g.L, d - start);
-        bulk_store(row + (size_t)start * HP4, src, (uint32_t)n1 * seg_bytes_site);
-        if (n1 < g.L) bulk_store(row, src + (uint32_t)n1 * seg_bytes_site, (uint32_t)(g.L - n1) * seg_bytes_site);
-        bulk_commit();
-      }
-    };
-
-    // history of flips accepted in the last STAGES-1 steps (for staleness of prefetched windows) and the flip whose
-    // stores may still be in flight
-    int hist_f[STAGES - 1];
-#pragma unroll
-    for (int i = 0; i < STAGES - 1; ++i) hist_f[i] = -1;
-    int pend_f = -1;
-    auto overlaps = [&](int fa, int fb) -> bool {
-      if (fa < 0 || fb < 0) return false;
-      int a2 = fa / d, a1 = fa - a2 * d, b2 = fb / d, b1 = fb - b2 * d;
-      return near_cyclic(a1, b1, g.L - 1, d) && near_cyclic(a2, b2, g.n_seg - 1, d);
-    };
-    auto proposal = [&](long long s, long long batch0) -> int {   // batch0 = index of the batch held in *_cur
-      int v0 = __shfl_sync(SO_FULL, f_cur, (int)(s & 31));
-      int v1 = __shfl_sync(SO_FULL, f_nxt, (int)(s & 31));
-      return ((s >> 5) == batch0) ? v0 : v1;
-    };
-
-    // prologue: windows of steps 0 .. STAGES-2 in flight
-    long long batch0 = 0;
-#pragma unroll
-    for (int i = 0; i < STAGES - 1; ++i)
-      if (i < P.n_steps) issue_loads(proposal(i, batch0), i);
-
-    int slot = 0;
-    for (long long s = 0; s < P.n_steps; ++s) {
-      if ((s >> 5) != batch0) {                      // entered the next batch of draws
-        batch0 = s >> 5;
-        f_cur = f_nxt; u_cur = u_nxt;
-        draw_batch(batch0 + 1, f_nxt, u_nxt);
-      }
-      const int f = __shfl_sync(SO_FULL, f_cur, (int)(s & 31));
-      const float u = __shfl_sync(SO_FULL, u_cur, (int)(s & 31));
-      const double T = __dmul_rn(tsc, __ldg(P.temps + s));
-
-      // prefetch step s+STAGES-1 into the stage freed by step s-1
-      {
-        long long sp = s + STAGES - 1;
-        if (sp < P.n_steps) {
-          int fp = proposal(sp, batch0);
-          int pslot = slot == 0 ? STAGES - 1 : slot - 1;
-          if (overlaps(fp, pend_f)) { bulk_wait_all(); pend_f = -1; }   // a store of that region may be in flight
-          issue_loads(fp, pslot);
+      // ---- 2. step s ---------------------------------------------------------------------------------------
+      if (s >= 0) {
+        const int fp = f_b;
+        const float u = u_b;
+        const int f1 = pk1(fp), f2 = pk2(fp);
+        const int f = f2 * d + f1;
+        bool stale = false;
+        if ((hist0 & hist1) != -1) {
+          if (hist0 >= 0) stale |= near_cyclic(f1, pk1(hist0), gL - 1, d) && near_cyclic(f2, pk2(hist0), gseg - 1, d);
+          if (hist1 >= 0) stale |= near_cyclic(f1, pk1(hist1), gL - 1, d) && near_cyclic(f2, pk2(hist1), gseg - 1, d);
         }
-      }
-      // is the prefetched window of step s stale?  (a flip accepted after its prefetch was issued overlaps it)
-      bool stale = false;
-#pragma unroll
-      for (int i = 0; i < STAGES - 1; ++i) stale |= overlaps(f, hist_f[i]);
-      const uint32_t bar = smem_u32(s_bar + slot);
-      mbar_wait(bar, (phase_bits >> slot) & 1u);
-      phase_bits ^= (1u << slot);
-      if (stale) {
-        bulk_wait_all();                             // all stores of this lane complete and visible
-        pend_f = -1;
-        __syncwarp();
-        issue_loads(f, slot);
-        mbar_wait(bar, (phase_bits >> slot) & 1u);
+        const int xbit = (s_bits[f >> 5] >> (f & 31)) & 1;
+        mbar_wait(bar0 + slot * 8, (phase_bits >> slot) & 1u);
         phase_bits ^= (1u << slot);
-      }
-
-      const int sgn = ((s_bits[f >> 5] >> (f & 31)) & 1) ? -1 : 1;
-      int4 *stg = s_stage + (size_t)slot * stage_i4;
-      long long acc = 0;
-      int4 hn[MAXIT];
-#pragma unroll
-      for (int it = 0; it < MAXIT; ++it) {
-        int q = lane + 32 * it;
-        if (q < Q) {
-          int4 h = stg[q];
-          int4 w = Wreg[it], w2 = s_w2[part[it]], n;
-          n.x = h.x + sgn * w.x; n.y = h.y + sgn * w.y; n.z = h.z + sgn * w.z; n.w = h.w + sgn * w.w;
-          acc += (long long)w2.x * (long long)(max(n.x, 0) - max(h.x, 0));
-          acc += (long long)w2.y * (long long)(max(n.y, 0) - max(h.y, 0));
-          acc += (long long)w2.z * (long long)(max(n.z, 0) - max(h.z, 0));
-          acc += (long long)w2.w * (long long)(max(n.w, 0) - max(h.w, 0));
-          hn[it] = n;
+        int4 *stg = s_stage + slot * stage_i4 + lane;
+        if (stale) {
+          bulk_wait_all();                          // lane 0: every store it issued is complete and visible
+          pend_f = -1;
+          __syncwarp();
+          reload_window_cold(stg - lane, hq, f1, f2, gb1, gb2, gL, Q, d, HP4, lane);
+          __syncwarp();
         }
-      }
-      // exact warp sum of int64 via three 21-bit limbs (each limb sum fits 32 bits)
-      {
-        int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
-        l0 = __reduce_add_sync(SO_FULL, l0);
-        l1 = __reduce_add_sync(SO_FULL, l1);
-        l2 = __reduce_add_sync(SO_FULL, l2);
-        acc = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
-      }
-      const double delta = so_real(k_c, sv.b2, k_sigma, sv.y_mean, acc >> SO_SPLIT_BITS, acc & SO_SPLIT_MASK, 0);
-      // Metropolis (OML/optimize_SA.py:108-116): fp32 pre-filter, fp64 rule when it cannot decide
-      bool accept, guard = false;
-      if (delta > 0.0) {
-        accept = true;
-        if (P.exact_guard && T <= 0.0 && delta < P.guard_tol) guard = true;
-      } else if (T > 0.0) {
-        float pf = __expf((float)delta / (float)T);
-        if (!P.exact_guard && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u)) {
-          accept = pf > u;
-        } else {
-          accept = exp(delta / T) > (double)u;
-          if (P.exact_guard && u > 0.f) guard = fabs(delta - T * log((double)u)) < P.guard_tol;
-        }
-      } else {
-        accept = false;
-        if (P.exact_guard && delta > -P.guard_tol) guard = true;
-      }
-      if (guard) {
-        double de = so_exact_delta(sv, s_bits, d, f, lane);
-        if (de > 0.0) accept = true;
-        else if (T > 0.0) accept = exp(de / T) > (double)u;
-        else accept = false;
-        ++n_guard;
-      }
-
-      if (accept) {
+        // delta-sum: D_j = sum over this lane's slots of relu(h + dw) - relu(h), dw = +-W (table chosen by the flip
+        // direction).  |D_j| <= sum_k |W1q[k][j]| < 2^31 by construction of the fixed-point grid, so int32 is exact.
+        const int4 *Wl = (xbit ? s_Wn : s_Wp) + lane;
+        int Dx = 0, Dy = 0, Dz = 0, Dw = 0;
 #pragma unroll
-        for (int it = 0; it < MAXIT; ++it)
-          if (lane + 32 * it < Q) stg[lane + 32 * it] = hn[it];
-        fence_async_smem();                          // generic-proxy writes -> visible to the bulk (async proxy) store
+        for (int it = 0; it < NSLOTS; ++it) {
+          const int off = (it == NSLOTS - 1) ? last_off : STRIDE * it;
+          const int4 h = stg[off];
+          const int4 w = Wl[off];
+          Dx += max(h.x + w.x, 0) - max(h.x, 0);
+          Dy += max(h.y + w.y, 0) - max(h.y, 0);
+          Dz += max(h.z + w.z, 0) - max(h.z, 0);
+          Dw += max(h.w + w.w, 0) - max(h.w, 0);
+        }
+        long long acc = (long long)w2.x * Dx + (long long)w2.y * Dy + (long long)w2.z * Dz + (long long)w2.w * Dw;
+        // exact warp sum of int64 via three 21-bit limbs (each limb sum fits 32 bits)
+        {
+          int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
+          l0 = __reduce_add_sync(SO_FULL, l0);
+          l1 = __reduce_add_sync(SO_FULL, l1);
+          l2 = __reduce_add_sync(SO_FULL, l2);
+          acc = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
+        }
+        // Metropolis (OML/optimize_SA.py:108-116).  fp32 fast path: delta = sigma*c*acc, sign from the exact integer;
+        // it decides unless p = exp(delta/T) is within 1e-3 (relative) of u -- then the fp64 rule (decide_cold).
+        bool accept;
+        {
+          const float Tf = tsc_f * t_b;
+          const bool up = sigma_pos ? (acc > 0) : (acc < 0);
+          const float pf = __expf(__fdividef((float)acc * k_f, Tf));
+          if (fast_ok && up && Tf > 0.f) {
+            accept = true;                          // delta > 0
+          } else if (fast_ok && !up && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u)) {
+            accept = pf > u;
+          } else {
+            int r = decide_cold(acc, P.sv.y_scale, P.sv.c, tsc, P.temps, s, u, P.exact_guard, P.guard_tol);
+            if (r & 2) {
+              r = exact_decision_cold(P.sv, s_bits, d, f, lane, __dmul_rn(tsc, __ldg(P.temps + s)), u);
+              ++n_guard;
+            }
+            accept = r & 1;
+          }
+        }
+        if (accept) {
+          asm volatile("" ::: "memory");            // re-read the stage rather than keeping updated values live
+#pragma unroll
+          for (int it = 0; it < NSLOTS; ++it) {
+            const int q = lane + STRIDE * it;
+            if (lane < STRIDE && q < Q) {
+              int4 h = stg[STRIDE * it];
+              const int4 w = Wl[STRIDE * it];
+              h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
+              stg[STRIDE * it] = h;
+            }
+          }
+          fence_async_smem();                       // generic-proxy writes -> visible to the bulk (async proxy) store
+          bulk_wait_all();                          // at most one flip's stores in flight (lane 0 owns the groups)
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t src = stage0 + slot * stage_pitch;
+            if (use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d)
+              tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
+            else
+              boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4);
+            bulk_commit();
+            s_bits[f >> 5] ^= (1u << (f & 31));
+            // the stage is re-used by the prefetch issued at the next step: the store must have read it by then
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          pend_f = fp;
+          lo += acc & SO_SPLIT_MASK;
+          hi += (acc >> SO_SPLIT_BITS) + (lo >> SO_SPLIT_BITS);
+          lo &= SO_SPLIT_MASK;
+          ++n_acc;
+        }
+        hist1 = hist0;
+        hist0 = accept ? fp : -1;
+        if (P.accept_out && lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
         __syncwarp();
-        bulk_wait_all();                             // at most one flip's stores in flight
-        issue_stores(f, slot);
-        pend_f = f;
-        if (lane == 0) s_bits[f >> 5] ^= (1u << (f & 31));
-        lo += acc & SO_SPLIT_MASK;
-        hi += (acc >> SO_SPLIT_BITS) + (lo >> SO_SPLIT_BITS);
-        lo &= SO_SPLIT_MASK;
-        ++n_acc;
       }
-#pragma unroll
-      for (int i = STAGES - 2; i > 0; --i) hist_f[i] = hist_f[i - 1];
-      hist_f[0] = accept ? f : -1;
-      if (P.accept_out && lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
-      // the stage is re-used by the prefetch issued at the next step: its stores must have read it by then
-      if (accept) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
+      f_b = f_a; u_b = u_a; t_b = t_a;
+      f_a = f_q; u_a = u_q; t_a = t_q;
       slot = slot + 1 == STAGES ? 0 : slot + 1;
     }
     bulk_wait_all();
@@ -319,10 +406,40 @@ __global__ void __launch_bounds__(WARPS * 32, 2) sa_window_kernel(SaParams P, Wi
 
 }  // namespace
 
+static int window_stage_i4(int Q) { return (Q + 3 + 7) & ~7; }
+
 size_t so_window_smem_bytes(int Q, int W, int stages) {
-  size_t i4 = 8 + (size_t)WARPS * stages * Q;
+  size_t st_i4 = window_stage_i4(Q);
+  size_t i4 = 8 + 2 * st_i4 + (size_t)WARPS * stages * st_i4;
   size_t words = ((size_t)WARPS * W + 3) & ~(size_t)3;
   return i4 * 16 + words * 4 + (size_t)WARPS * stages * 8 + 16;
+}
+
+template <int HP4, int NSLOTS>
+static int launch_window(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks, cudaStream_t st) {
+  auto kern = sa_window_kernel<HP4, NSLOTS>;
+  SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)c->sur->Wst_dev, c->tmap);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+
+template <int HP4>
+static int launch_window_hp4(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks,
+                             cudaStream_t st) {
+  switch (g.nslots) {
+    case 1: return launch_window<HP4, 1>(c, P, g, smem, blocks, st);
+    case 2: return launch_window<HP4, 2>(c, P, g, smem, blocks, st);
+    case 3: return launch_window<HP4, 3>(c, P, g, smem, blocks, st);
+    case 4: return launch_window<HP4, 4>(c, P, g, smem, blocks, st);
+    case 5: return launch_window<HP4, 5>(c, P, g, smem, blocks, st);
+    case 6: return launch_window<HP4, 6>(c, P, g, smem, blocks, st);
+    case 7: return launch_window<HP4, 7>(c, P, g, smem, blocks, st);
+    case 8: return launch_window<HP4, 8>(c, P, g, smem, blocks, st);
+    case 9: return launch_window<HP4, 9>(c, P, g, smem, blocks, st);
+    case 10: return launch_window<HP4, 10>(c, P, g, smem, blocks, st);
+    default: so_set_error("window too large for the pipelined kernel"); return SO_EINVAL;
+  }
 }
 
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st) {
@@ -331,23 +448,24 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
   WinGeom g;
   g.b1 = s->win_b1; g.b2 = s->win_b2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
+  g.use_tma = c->tmap_ok;
   const int Q = s->K * s->HP4;
-  constexpr int STAGES = 3;
-  size_t smem = so_window_smem_bytes(Q, P.W, STAGES);
+  const int stride = (32 / s->HP4) * s->HP4;
+  g.stage_i4 = window_stage_i4(Q);
+  g.nslots = (Q + stride - 1) / stride;
+  size_t smem = so_window_smem_bytes(Q, P.W, 3);
   long long want = (P.n_chains + WARPS - 1) / WARPS;
   int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
   if (blocks < 1) blocks = 1;
-#define SO_WIN_CASE(HP4V)                                                                                        \
-  case HP4V: {                                                                                                   \
-    auto kern = sa_window_kernel<HP4V, STAGES>;                                                                  \
-    SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)s->Wst_dev);                                      \
-  } break;
   switch (s->HP4) {
-    SO_WIN_CASE(1) SO_WIN_CASE(2) SO_WIN_CASE(3) SO_WIN_CASE(4) SO_WIN_CASE(5) SO_WIN_CASE(6) SO_WIN_CASE(7) SO_WIN_CASE(8)
+    case 1: return launch_window_hp4<1>(c, P, g, smem, blocks, st);
+    case 2: return launch_window_hp4<2>(c, P, g, smem, blocks, st);
+    case 3: return launch_window_hp4<3>(c, P, g, smem, blocks, st);
+    case 4: return launch_window_hp4<4>(c, P, g, smem, blocks, st);
+    case 5: return launch_window_hp4<5>(c, P, g, smem, blocks, st);
+    case 6: return launch_window_hp4<6>(c, P, g, smem, blocks, st);
+    case 7: return launch_window_hp4<7>(c, P, g, smem, blocks, st);
+    case 8: return launch_window_hp4<8>(c, P, g, smem, blocks, st);
     default: so_set_error("hidden width not supported"); return SO_EINVAL;
   }
-#undef SO_WIN_CASE
-  SO_CUDA(cudaGetLastError());
-  return SO_OK;
 }
