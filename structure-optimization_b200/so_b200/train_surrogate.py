@@ -1,0 +1,122 @@
+"""
+surrogate -- drop-in for OML/train_surrogate.py:15-184.  Training stays on the host with scikit-learn (the weights'
+source named by the task); the evaluate side (eval_structure_rate, called `eval_rate` by optimize()) runs on the GPU.
+Upstream defects resolved as in SURVEY 9.5: `Y_scaler` is stored, `train` takes self, both method names exist.
+"""
+import numpy as np
+from . import engine
+
+
+def descriptor_offsets(K, d):
+    """Site offsets of the K descriptor columns: full translation row (K == N) or the 7x7 local window (K == 49)."""
+    if K == d * d:
+        return engine.full_offsets(d)
+    if K == 49:
+        return engine.local_offsets(3)
+    raise ValueError('descriptor width %d is neither the full translation row (%d) nor the 7x7 local window' % (K, d * d))
+
+
+def flatten_tree(classifier):
+    """sklearn DecisionTreeClassifier -> arrays for so_surrogate_create (leaf iff feature < 0; left iff x <= thr)."""
+    t = classifier.tree_
+    cls = np.asarray(classifier.classes_)
+    leaf_cls = cls[np.argmax(t.value[:, 0, :], axis=1)]
+    return dict(feature=t.feature.astype(np.int32), thr=t.threshold.astype(np.float64),
+                left=t.children_left.astype(np.int32), right=t.children_right.astype(np.int32),
+                active=(leaf_cls == 1.0).astype(np.uint8))
+
+
+def tables_for(surr, lattice, gate=True):
+    """Device tables of any reference-style fitted surrogate (duck type: predictor, Y_scaler, classifier)."""
+    mlp = surr.predictor
+    if getattr(mlp, 'out_activation_', 'identity') != 'identity' or len(mlp.coefs_) != 2:
+        raise ValueError('the surrogate must be a single-hidden-layer MLPRegressor (train_surrogate.py:150-151)')
+    W1 = np.asarray(mlp.coefs_[0], dtype=np.float64)
+    clf = getattr(surr, 'classifier', None) if gate else None
+    scaler = getattr(surr, 'Y_scaler', None)
+    y_mean = float(scaler.mean_[0]) if scaler is not None else 0.0
+    y_scale = float(scaler.scale_[0]) if scaler is not None else 1.0
+    return engine.SurrogateTables(lattice, descriptor_offsets(W1.shape[0], lattice.d), W1, mlp.intercepts_[0],
+                                  np.asarray(mlp.coefs_[1]).reshape(-1), float(np.asarray(mlp.intercepts_[1]).reshape(-1)[0]),
+                                  y_mean, y_scale, flatten_tree(clf) if clf is not None else None)
+
+
+class surrogate(object):
+    """Surrogate model replacing KMC evaluation (OML/train_surrogate.py:15-31)."""
+
+    def __init__(self, device=0):
+        self.cat = None
+        self.predictor = None
+        self.classifier = None
+        self.Y_scaler = None
+        self.all_syms = None
+        self.X_reg = None
+        self.Y_reg = None
+        self.site_is_active = None
+        self._device = device
+        self._tables = None
+
+    # ---- evaluate (GPU) -----------------------------------------------------------------------------------
+    def _get_tables(self, K):
+        if self._tables is None:
+            if self.cat is not None:
+                lattice = self.cat._lattice
+            else:
+                d = int(round(np.sqrt(K)))
+                lattice = engine.Lattice(d if d * d == K and d >= 7 else 12, "LSC", device=self._device)
+            self._tables = tables_for(self, lattice)
+        return self._tables
+
+    def eval_structure_rate(self, all_trans, normalize=False):
+        """OML/train_surrogate.py:34-54: gate, MLP, inverse Y scaling, sum over active rows."""
+        all_trans = np.asarray(all_trans)
+        active, rate = self._get_tables(all_trans.shape[1]).eval_rows(all_trans)
+        if not active.any():
+            return 0
+        total = np.sum(rate[active])
+        return total / len(all_trans) if normalize else total
+
+    eval_rate = eval_structure_rate          # the name optimize() calls (OML/optimize_SA.py:42,102)
+
+    def eval_site_rate(self, all_trans, normalize=False):
+        active, rate = self._get_tables(np.asarray(all_trans).shape[1]).eval_rows(all_trans)
+        return np.where(active, rate, 0.0)
+
+    # ---- train (host, scikit-learn; OML/train_surrogate.py:61-152) --------------------------------------------
+    def train(self, structure_occs, site_rates, curr_fldr=None, max_iter=10000, random_state=None, verbose=False):
+        self.all_syms = np.asarray(structure_occs)
+        self.partition_data_set(np.asarray(site_rates))
+        self.train_classifier()
+        self.train_regressor(max_iter=max_iter, random_state=random_state, verbose=verbose)
+        self._tables = None
+
+    def partition_data_set(self, site_rates):
+        flat = np.transpose(np.tile(site_rates.flatten(), [3, 1])).flatten()      # one copy per rotation
+        y_max = np.max(flat)
+        if y_max == 0.:
+            raise NameError('No active sites in database.')
+        self.site_is_active = (flat > 0.06 * y_max).astype(float)
+        self.X_reg = self.all_syms[self.site_is_active == 1]
+        self.Y_reg = flat[self.site_is_active == 1]
+
+    def train_classifier(self):
+        from sklearn import tree
+        from sklearn.model_selection import train_test_split
+        self.classifier = tree.DecisionTreeClassifier(max_depth=30, random_state=0)
+        X_train, X_test, y_train, y_test = train_test_split(self.all_syms, self.site_is_active, random_state=0)
+        self.classifier.fit(X_train, y_train)
+        self.frac_wrong_train = float(np.sum(np.abs(self.classifier.predict(X_train) - y_train))) / len(y_train)
+        self.frac_wrong_test = float(np.sum(np.abs(self.classifier.predict(X_test) - y_test))) / len(y_test)
+
+    def train_regressor(self, reg_parity_fname=None, max_iter=10000, random_state=None, verbose=False):
+        from sklearn.neural_network import MLPRegressor
+        from sklearn.preprocessing import StandardScaler
+        self.Y_scaler = StandardScaler(with_mean=True, with_std=True)
+        self.Y_scaler.fit(self.Y_reg.reshape(-1, 1))
+        Y = self.Y_scaler.transform(self.Y_reg.reshape(-1, 1)).flatten()
+        self.predictor = MLPRegressor(activation='relu', verbose=verbose, learning_rate_init=0.0001, alpha=0.1,
+                                      hidden_layer_sizes=(20,), max_iter=max_iter, tol=0.00001,
+                                      random_state=random_state)
+        self.predictor.fit(self.X_reg, Y)
+        pred = self.Y_scaler.inverse_transform(self.predictor.predict(self.X_reg).reshape(-1, 1)).flatten()
+        self.mean_abs_error = float(np.mean(np.abs(pred - self.Y_reg)))
