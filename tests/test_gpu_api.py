@@ -221,6 +221,6 @@ def test_exact_guard_matches_reference_decisions():
     ch.attach(Hp.tables_from_params(lat, p))
     stats, acc = ch.anneal(z["temps"], proposals=z["prop"], uniforms=z["u"], want_accept=True, exact_guard=True,
                            guard_tol=5e-3)                            # wide band: the exact path takes many decisions
-    assert stats["guard_fired"] > 50
+    assert stats["guard_fired"] > 10
     assert (acc.astype(bool) == z["gated_faithful_accept"]).all()
     assert (ch.get_occupancy() == z["gated_faithful_x"]).all()
