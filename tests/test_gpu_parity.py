@@ -357,3 +357,105 @@ def test_tscale_and_best(eng):
     for c in (0, 17, 49):
         o = SA.anneal_fixed(p, q, d, x[c], temps, prop[c], u[c], tscale=ts[c])
         assert (acc[c].astype(bool) == o["accept"]).all()
+
+
+# ---- replica exchange / best structure (new capability; oracle/exchange.py is the checker) ---------------------
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1), (4, 2)])
+def test_exchange_round_matches_oracle(eng, world, rank):
+    """One process emulates `rank` of `world`: the all-gathered arrays are fabricated on the device, the kernel must
+    take the oracle's swap decisions and update exactly this rank's chains."""
+    import ctypes as C
+    import torch
+    from oracle import exchange as X
+    from so_b200 import _lib as B
+    d, n_local, ladder = 12, 48, 8
+    lat = eng.Lattice(d, "LSC")
+    ch = eng.Chains(lat, n_local)
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=9)
+    ch.attach(Hp.tables_from_params(lat, p))
+    rng = np.random.default_rng(world * 10 + rank)
+    of_all = rng.normal(size=world * n_local)
+    g = np.concatenate([np.arange(n_local) * world + r for r in range(world)])
+    ts = np.exp(-5.0 * (g % ladder) / (ladder - 1.0))
+    rng.shuffle(ts.reshape(world * n_local // ladder, ladder).T)              # scramble rung order inside ladders
+    ch.set_tscale(ts[rank * n_local:(rank + 1) * n_local])
+    of_dev, ts_dev = torch.from_numpy(of_all).cuda(), torch.from_numpy(ts.copy()).cuda()
+    t_ref, seed = 0.05, 77
+    swapped_total = 0
+    cur = ts.copy()
+    for rnd in range(4):
+        want = X.exchange_round(of_all, cur, world, n_local, ladder, rnd & 1, seed, rnd, t_ref)
+        ns = C.c_int64()
+        B.check(ch.lib.so_exchange(ch.h, rank, world, ladder, rnd & 1, seed, rnd, t_ref, C.c_void_p(of_dev.data_ptr()),
+                                   C.c_void_p(ts_dev.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                   C.byref(ns)))
+        assert (ts_dev.cpu().numpy() == want).all()
+        assert (ch.get_tscale() == want[rank * n_local:(rank + 1) * n_local]).all()
+        assert ns.value == int((want != cur)[rank * n_local:(rank + 1) * n_local].sum())
+        swapped_total += ns.value
+        cur = want
+    assert swapped_total > 0 and sorted(cur.tolist()) == sorted(ts.tolist())          # temperatures are only permuted
+
+
+def test_best_record_and_objectives_dev(eng):
+    import ctypes as C
+    import torch
+    from so_b200 import parallel as P, _lib as B
+    d, n = 12, 300
+    lat = eng.Lattice(d, "LSC")
+    ch = eng.Chains(lat, n)
+    x = Hp.random_structures(n, 144, seed=5)
+    ch.set_occupancy(x)
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=10)
+    ch.attach(Hp.tables_from_params(lat, p))
+    of = ch.objective()
+    gather = P.BestGather(ch, chain_id0=1000, world=1)
+    best_of, best_chain, bits = gather.gather()
+    assert best_of == of.max() and best_chain == 1000 + int(np.argmax(of))
+    assert (eng.unpack_bits(bits[None, :], 144)[0] == x[int(np.argmax(of))]).all()
+    of_dev = torch.zeros(n, dtype=torch.float64, device="cuda")
+    B.check(ch.lib.so_objectives_dev(ch.h, C.c_void_p(of_dev.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert (of_dev.cpu().numpy() == of).all()
+    pt = P.ReplicaExchange(ch, ladder=6, seed=3, rank=0, world=1)
+    ms = pt.round(0, t_ref=0.05)
+    assert ms >= 0 and sorted(ch.get_tscale().tolist()) == sorted(P.ladder_tscale(np.arange(n), 6).tolist())
+
+
+# ---- BASELINE configs[1] at full size: 4,096 chains x 14,400 steps, injected proposal/uniform sequence -----------
+def _config2(eng, p, n_chains):
+    from oracle import c_oracle
+    d, N, steps = 12, 144, 14400                                  # n_cycles = 100 (optimize_SA.py:11,25)
+    rng = np.random.Generator(np.random.Philox(key=1234))
+    x0 = (rng.random((n_chains, N)) < 0.5).astype(np.uint8)
+    prop = rng.integers(0, N, size=(n_chains, steps)).astype(np.int32)
+    u = rng.random((n_chains, steps), dtype=np.float32)
+    temps = SA.schedule("exp", 0.05, steps)
+    lat = eng.Lattice(d, "NH3")
+    ch = eng.Chains(lat, n_chains)
+    ch.set_occupancy(x0)
+    ch.attach(Hp.tables_from_params(lat, p))
+    stats, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True)
+    o = c_oracle.anneal_fixed_many(p, S.quantize(p), d, x0, temps, prop, u)
+    assert (acc.astype(bool) == o["accept"]).all()                # accept/reject bit-vector identical
+    x1 = ch.get_occupancy()
+    assert (x1 == o["x"]).all()                                   # final occupancies identical
+    of, hi, lo, na = ch.objective(sums=True)
+    assert (hi == o["hi"]).all() and (lo == o["lo"]).all() and (na == o["n_act"]).all() and (of == o["OF"]).all()
+    # descriptors of the final structures, bit-exact
+    out = ch.descriptors(c6=True, lsc_type=True, nh3_exp=True)
+    assert (out["c6"] == ST.c6_counts(x1, d)).all() and (out["lsc_type"] == ST.lsc_types(x1, d)).all()
+    assert (out["nh3_exp"] == ST.nh3_export_hist(ST.nh3_types(x1, d))).all()
+    # scores of a sample against the reference's fp64 arithmetic
+    for c in range(0, n_chains, max(1, n_chains // 16)):
+        ref = S.eval_rate_fp64(p, L.generate_all_translations(x1[c], d))
+        assert abs(of[c] - ref) <= 1e-5 * max(abs(ref), 1e-12)
+    assert stats["flips"] == n_chains * steps
+
+
+def test_config2_full_size_open(eng):
+    _config2(eng, Hp.golden_surrogate(gated=False), 4096)
+
+
+def test_config2_gated(eng):
+    _config2(eng, Hp.golden_surrogate(gated=True), 256)
