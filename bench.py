@@ -296,7 +296,7 @@ def run_gpu(a):
         "data": "synthetic", "config": workload_config(a),
         "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sa_window_kernel<5,3>",
+                     "traffic": traffic, "kernel": "sa_window_kernel<5,9>",
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "launch_ms": kern_ms / a.steps},
     }
