@@ -107,10 +107,18 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def _one_thread_per_worker():
+    """One chain per core, as the reference runs one structure per MPI rank: keep each worker's BLAS single-threaded
+    (otherwise cores x cores threads oversubscribe the host and the baseline is unfairly slow)."""
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+
+
 def cpu_reference_rate(d, flips_per_core, cores, total_steps):
     """flip-evals/s of the reference CPU path with one independent chain per host core
     (drivers/Online_learn_main.py:108-114 runs one structure per MPI rank)."""
     import multiprocessing as mp
+    _one_thread_per_worker()
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_worker, [(i, d, 2, total_steps, 0) for i in range(cores)])      # warm-up (imports, BLAS)
@@ -129,6 +137,7 @@ def run_reference(a):
     total = (a.warmup + a.steps) * d * d
     flips = a.ref_flips
     import multiprocessing as mp
+    _one_thread_per_worker()
     ctx = mp.get_context("spawn")
     per_step = []
     with ctx.Pool(cores) as pool:
@@ -330,8 +339,8 @@ def main():
     ap.add_argument("--pt", action="store_true", help="parallel tempering (BASELINE configs[4]): fixed ladders + swaps")
     ap.add_argument("--ladder", type=int, default=8, help="parallel-tempering ladder size")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-flips", type=int, default=400, help="Metropolis steps per core for the CPU baseline (0 = skip)")
-    ap.add_argument("--ref-flips", type=int, default=100, help="Metropolis steps per core per bench step, --impl reference")
+    ap.add_argument("--cpu-flips", type=int, default=3000, help="Metropolis steps per core for the CPU baseline (0 = skip)")
+    ap.add_argument("--ref-flips", type=int, default=1000, help="Metropolis steps per core per bench step, --impl reference")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -459,3 +459,50 @@ def test_config2_full_size_open(eng):
 
 def test_config2_gated(eng):
     _config2(eng, Hp.golden_surrogate(gated=True), 256)
+
+
+# ---- BASELINE configs[3] shape (96x96, local 7x7 MLP): oracle parity on a sample + size-independent properties -----
+def test_config4_lattice_96(eng):
+    from oracle import c_oracle
+    d, N, n_chains, steps = 96, 9216, 2048, 1500
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=0)
+    q = S.quantize(p)
+    lat = eng.Lattice(d, "NH3")
+    tab = Hp.tables_from_params(lat, p)
+    ch = eng.Chains(lat, n_chains)
+    ch.randomize(seed=1234, coverage=0.5)
+    x0 = ch.get_occupancy()
+    ch.attach(tab)
+    temps = SA.schedule("exp", 0.3, steps)
+    seed, chain_id0, step0 = 99, 70000, 11
+    stats, acc = ch.anneal(temps, step0=step0, seed=seed, chain_id0=chain_id0, want_accept=True)
+    x1 = ch.get_occupancy()
+    of, hi, lo, na = ch.objective(sums=True)
+    # (1) oracle parity on a sample of chains, with the Philox draws restated by the oracle
+    sample = np.arange(0, n_chains, 97)
+    prop, u = philox.draws(seed, (chain_id0 + sample)[:, None], (step0 + np.arange(steps))[None, :], N)
+    o = c_oracle.anneal_fixed_many(p, q, d, x0[sample], temps, prop, u)
+    assert (acc[sample].astype(bool) == o["accept"]).all() and (x1[sample] == o["x"]).all()
+    assert (hi[sample] == o["hi"]).all() and (lo[sample] == o["lo"]).all() and (of[sample] == o["OF"]).all()
+    # (2) state invariant on ALL chains: tracked sums and first-layer state == fresh recompute from the final bits
+    fresh = ch.score()
+    assert (fresh == of).all()
+    again = ch.objective(sums=True)
+    assert (again[1] == hi).all() and (again[2] == lo).all()
+    # (3) flip bookkeeping: every chain's Hamming distance to its start has the parity of its accepted-flip count
+    assert ((x0 != x1).sum(1) % 2 == acc.sum(1) % 2).all()
+    # (4) determinism: same seed and counters -> same bits (counter-based RNG, no atomics in the data path)
+    ch.set_occupancy(x0)
+    ch.anneal(temps, step0=step0, seed=seed, chain_id0=chain_id0)
+    assert (ch.get_occupancy() == x1).all()
+    # (5) segmentation invariance: the same steps in three launches give the same result (resume is exact)
+    ch.set_occupancy(x0)
+    for a, b in ((0, 400), (400, 401), (401, steps)):
+        ch.anneal(temps[a:b], step0=step0 + a, seed=seed, chain_id0=chain_id0)
+    assert (ch.get_occupancy() == x1).all()
+    # (6) site types of the final structures bit-exact on a sample, histograms consistent on all chains
+    out = ch.descriptors(chain0=0, n=n_chains, lsc_hist=True, nh3_hist=True, nh3_exp=True)
+    assert (out["lsc_hist"].sum(1) == N).all() and (out["nh3_hist"].sum(1) == 5 * N).all()
+    assert (out["nh3_exp"][:, 1:] == out["nh3_hist"][:, [1, 3, 5, 16, 17, 18, 19]]).all()
+    t = ch.descriptors(chain0=5, n=3, nh3_type=True, lsc_type=True)
+    assert (t["nh3_type"] == ST.nh3_types(x1[5:8], d)).all() and (t["lsc_type"] == ST.lsc_types(x1[5:8], d)).all()
