@@ -326,8 +326,43 @@ def run_gpu(a):
         dist.destroy_process_group()
 
 
+def run_batch_score(a):
+    """BASELINE configs[2]: batch scoring of random Ni/Pt occupancy structures (eval_init_structures analogue, no
+    annealing) on one B200: surrogate rate + LSC and NH3-exported site-type histograms per structure."""
+    import torch
+    from so_b200 import engine
+    d = a.d if a.d != D else 12
+    N = d * d
+    n = a.structures
+    rng = np.random.default_rng(2)
+    cov = rng.random((n, 1))
+    x = (rng.random((n, N)) < cov).astype(np.uint8)                 # randomize(coverage=None), dynamic_cat.py:73-76
+    bits = engine.pack_bits(x)
+    lat = engine.Lattice(d, "NH3", device=0)
+    offsets = engine.full_offsets(d) if d <= 16 else engine.local_offsets(3)
+    W1, b1, w2, b2 = glorot_mlp(offsets, H, 0)
+    tab = engine.SurrogateTables(lat, offsets, W1, b1, w2, b2)
+    for _ in range(a.warmup):
+        tab.score_batch(bits[:65536], want_lsc_hist=True, want_nh3_exp=True)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        rate, lh, ne = tab.score_batch(bits, want_lsc_hist=True, want_nh3_exp=True)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    print(json.dumps({"metric": "structures scored/sec (host buffers in, host results out)", "value": n / dt,
+                      "unit": "structures/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt,
+                      "higher_is_better": True, "data": "synthetic", "dtype": "int32 fixed-point / int64 sums",
+                      "config": {"workload": "BASELINE configs[2]: %d random structures, %dx%d, %s descriptor MLP %d->20->1 "
+                                             "+ LSC / NH3-exported histograms" % (n, d, d, "full" if d <= 16 else "local7x7",
+                                                                                  len(offsets)),
+                                 "checksum_rate": float(rate.sum()), "checksum_hist": int(lh.sum() + ne.sum())},
+                      "h2d_bytes_per_step": int(bits.nbytes), "d2h_bytes_per_step": int(rate.nbytes + lh.nbytes + ne.nbytes)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="anneal", choices=["anneal", "score"])
+    ap.add_argument("--structures", type=int, default=1 << 20)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -344,6 +379,8 @@ def main():
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "score":
+        run_batch_score(a)
     else:
         run_gpu(a)
 

@@ -506,3 +506,29 @@ def test_config4_lattice_96(eng):
     assert (out["nh3_exp"][:, 1:] == out["nh3_hist"][:, [1, 3, 5, 16, 17, 18, 19]]).all()
     t = ch.descriptors(chain0=5, n=3, nh3_type=True, lsc_type=True)
     assert (t["nh3_type"] == ST.nh3_types(x1[5:8], d)).all() and (t["lsc_type"] == ST.lsc_types(x1[5:8], d)).all()
+
+
+# ---- BASELINE configs[2]: batch scoring, no annealing ---------------------------------------------------------------
+def test_batch_scoring_large(eng):
+    d, N, n = 12, 144, 1 << 18
+    rng = np.random.default_rng(2)
+    x = (rng.random((n, N)) < rng.random((n, 1))).astype(np.uint8)
+    x[0], x[1] = 0, 1                                               # empty and full lattice
+    p = Hp.golden_surrogate(gated=True)
+    lat = eng.Lattice(d, "NH3")
+    tab = Hp.tables_from_params(lat, p)
+    rate, lh, ne = tab.score_batch(eng.pack_bits(x), want_lsc_hist=True, want_nh3_exp=True)
+    q = S.quantize(p)
+    for c in list(range(0, 64)) + list(range(64, n, n // 97)):      # oracle parity on a sample, bit-exact
+        assert rate[c] == S.score_fixed(p, q, x[c], d)[0]
+    lsc = ST.lsc_types(x[:2048], d)
+    assert (lh[:2048] == np.stack([(lsc == t).sum(1) for t in range(3)], 1)).all()
+    assert (ne[:2048] == ST.nh3_export_hist(ST.nh3_types(x[:2048], d))).all()
+    # size-independent properties on ALL structures: histogram totals; translation invariance (a translated structure
+    # has the same multiset of descriptor rows, hence bit-identical exact sums and the same site-type histograms)
+    assert (lh.sum(1) == N).all() and (ne.sum(1) == 5 * N).all()
+    xs = np.roll(x.reshape(n, d, d), shift=(5, 3), axis=(1, 2)).reshape(n, N)
+    rate2, lh2, ne2 = tab.score_batch(eng.pack_bits(xs), want_lsc_hist=True, want_nh3_exp=True)
+    assert (rate2 == rate).all() and (lh2 == lh).all() and (ne2 == ne).all()
+    ref = S.eval_rate_fp64(p, L.generate_all_translations(x[7], d))
+    assert abs(rate[7] - ref) <= 1e-5 * max(abs(ref), 1e-12)
