@@ -331,7 +331,7 @@ def run_batch_score(a):
     annealing) on one B200: surrogate rate + LSC and NH3-exported site-type histograms per structure."""
     import torch
     from so_b200 import engine
-    d = a.d if a.d != D else 12
+    d = a.score_d
     N = d * d
     n = a.structures
     rng = np.random.default_rng(2)
@@ -363,6 +363,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="anneal", choices=["anneal", "score"])
     ap.add_argument("--structures", type=int, default=1 << 20)
+    ap.add_argument("--score-d", type=int, default=12, help="lattice edge of the batch-scoring workload")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
