@@ -303,7 +303,9 @@ def run_gpu(a):
         "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed-point state / int64 sums / f64 Metropolis",
         "data": "synthetic", "config": workload_config(a),
-        "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": a.steps,
+        "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e,
+        # SA kernel per sweep (+ arg-max kernel of the all-gather, + objective/decision/commit kernels of a swap round)
+        "gpu_launches": a.steps * (1 + (1 if gather is not None else 0) + (3 if pt is not None else 0)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "sa_window_kernel<5,9>",
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
