@@ -224,3 +224,24 @@ def test_exact_guard_matches_reference_decisions():
     assert stats["guard_fired"] > 10
     assert (acc.astype(bool) == z["gated_faithful_accept"]).all()
     assert (ch.get_occupancy() == z["gated_faithful_x"]).all()
+
+
+def test_database_formats_roundtrip(tmp_path):
+    """Files either side of the path (KMC_handler.py:13-55, Online_learn_main.py:26-47, generate_init_structures.py)."""
+    from so_b200 import LSC_cat
+    from so_b200.database import make_random_structure, write_structure_files, read_database
+    cat = LSC_cat(12)
+    folders = []
+    for i in (4, 11):
+        fldr = os.path.join(str(tmp_path), 'structure_%d' % i)
+        x = make_random_structure(i, 48, cat, fldr)
+        assert (np.array(x) == LA.make_random_structure(i, 48, 12)).all()          # same seeded recipe as upstream
+        assert (np.load(os.path.join(fldr, 'occupancies.npy')) == np.array(x)).all()
+        sym = np.load(os.path.join(fldr, 'occ_symmetries.npy'))
+        assert sym.shape == (432, 144) and (sym == L.generate_all_translations_and_rotations(np.array(x), 12)).all()
+        assert os.path.isfile(os.path.join(fldr, 'lattice_input.dat'))
+        np.save(os.path.join(fldr, 'site_rates.npy'), cat.compute_site_rates_lsc())
+        folders.append(fldr)
+    os.makedirs(os.path.join(str(tmp_path), 'unfinished'))
+    occs, rates = read_database(folders + [os.path.join(str(tmp_path), 'unfinished')])
+    assert occs.shape == (864, 144) and rates.shape == (2, 144)
