@@ -149,6 +149,15 @@ int so_anneal(so_chains *c, const so_anneal_args *args, so_anneal_stats *stats);
 int so_set_tscale(so_chains *c, int64_t chain0, int64_t n, const double *tscale);
 int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale);
 
+/* ---- analytical objective of the LSC toy model.
+ *      so_lsc_analytical: LSC_cat.compute_site_rates_lsc / eval_struc_rate_anal (OML/LSC_cat.py:248-316) of the current
+ *      occupancies of chains [chain0, chain0+n): site_rates[n][N] and/or struct_rate[n] (either may be NULL).
+ *      so_anneal_analytical: the loop of optimize(mode='analytical') (OML/optimize_SA.py:59-132, objective :104) with
+ *      the same arguments as so_anneal (exact_guard / variant ignored); of_out[n_chains] = final objective or NULL.
+ *      The dense steady-state system lives in shared memory: lattices up to 160 sites (d <= 12).              */
+int so_lsc_analytical(so_chains *c, int64_t chain0, int64_t n, double *site_rates, double *struct_rate);
+int so_anneal_analytical(so_chains *c, const so_anneal_args *args, so_anneal_stats *stats, double *of_out);
+
 /* ---- best structure + replica exchange (new capability; not in the reference)               */
 /* arg-max of the tracked objective over local chains; bits[words] may be NULL                            */
 int so_best(so_chains *c, double *of_out, int64_t *chain_out, uint32_t *bits);

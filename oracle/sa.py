@@ -155,3 +155,31 @@ def anneal_fixed(p, q, d, x0, temps, prop, u, tscale=1.0, margins=False):
     if margins:
         out["margin"] = margin
     return out
+
+
+def optimize_analytical(x0, d, temps, prop, u):
+    """optimize(mode='analytical') for ONE chain (OML/optimize_SA.py:43-44,103-116 with OML/LSC_cat.py:248-316)."""
+    from . import lsc_analytical as LA
+    x = np.asarray(x0, dtype=np.uint8).copy()
+    OF = LA.eval_struc_rate_anal(x, d)
+    accept_log = np.zeros(len(temps), dtype=bool)
+    margin = np.full(len(temps), np.inf)
+    for s in range(len(temps)):
+        f = int(prop[s])
+        x[f] ^= 1
+        OF_new = LA.eval_struc_rate_anal(x, d)
+        delta = OF_new - OF
+        if delta > 0:
+            acc = True
+        elif temps[s] > 0:
+            pr = math.exp(delta / temps[s])
+            acc = pr > float(u[s])
+            margin[s] = abs(pr - float(u[s]))
+        else:
+            acc = False
+        if acc:
+            OF = OF_new
+        else:
+            x[f] ^= 1
+        accept_log[s] = acc
+    return dict(x=x, OF=float(OF), accept=accept_log, margin=margin)

@@ -753,6 +753,76 @@ int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale) {
   return SO_OK;
 }
 
+// ---- LSC analytical objective ------------------------------------------------------------------------------
+int so_lsc_analytical(so_chains *c, int64_t chain0, int64_t n, double *site_rates, double *struct_rate) {
+  SO_TRY(check_range(c, chain0, n));
+  const so_lattice *L = c->lat;
+  SO_REQUIRE(L->N <= so_lsc_max_sites(), "the analytical objective is limited to %d sites (this lattice has %d)",
+             so_lsc_max_sites(), L->N);
+  if (n == 0) return SO_OK;
+  SO_CUDA(cudaSetDevice(L->device));
+  DevBuf d_sr, d_rate;
+  if (site_rates) SO_TRY(d_sr.alloc((size_t)n * L->N * 8));
+  if (struct_rate) SO_TRY(d_rate.alloc((size_t)n * 8));
+  SO_TRY(so_launch_lsc_analytical(L, c->bits_dev + chain0 * L->W, n, d_sr.as<double>(), d_rate.as<double>(), c->stream));
+  if (site_rates) SO_CUDA(cudaMemcpyAsync(site_rates, d_sr.p, (size_t)n * L->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (struct_rate) SO_CUDA(cudaMemcpyAsync(struct_rate, d_rate.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  SO_CUDA(cudaStreamSynchronize(c->stream));
+  return SO_OK;
+}
+
+int so_anneal_analytical(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats, double *of_out) {
+  SO_REQUIRE(c && a, "NULL argument");
+  const so_lattice *L = c->lat;
+  SO_REQUIRE(L->N <= so_lsc_max_sites(), "the analytical objective is limited to %d sites (this lattice has %d)",
+             so_lsc_max_sites(), L->N);
+  SO_REQUIRE(a->n_steps >= 0 && a->step0 >= 0, "negative step range");
+  SO_REQUIRE(a->temps || a->n_steps == 0, "temps is NULL");
+  SO_REQUIRE((a->proposals == nullptr) == (a->uniforms == nullptr), "proposals and uniforms must be given together");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  SO_CUDA(cudaSetDevice(L->device));
+  const size_t ns = (size_t)a->n_steps, nc = (size_t)c->n_chains;
+  if (a->proposals)
+    for (size_t i = 0; i < nc * ns; ++i)
+      SO_REQUIRE(a->proposals[i] >= 0 && a->proposals[i] < L->N, "proposal %zu = %d out of range", i, a->proposals[i]);
+  DevBuf d_temps, d_prop, d_uni, d_acc, d_of;
+  SO_TRY(d_temps.alloc(ns * 8));
+  if (ns) SO_CUDA(cudaMemcpyAsync(d_temps.p, a->temps, ns * 8, cudaMemcpyHostToDevice, c->stream));
+  if (a->proposals) {
+    SO_TRY(d_prop.alloc(nc * ns * 4));
+    SO_TRY(d_uni.alloc(nc * ns * 4));
+    SO_CUDA(cudaMemcpyAsync(d_prop.p, a->proposals, nc * ns * 4, cudaMemcpyHostToDevice, c->stream));
+    SO_CUDA(cudaMemcpyAsync(d_uni.p, a->uniforms, nc * ns * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (a->accept_out) SO_TRY(d_acc.alloc(nc * ns));
+  SO_TRY(d_of.alloc(nc * 8));
+  SO_CUDA(cudaMemsetAsync(c->counters_dev, 0, 3 * sizeof(unsigned long long), c->stream));
+  SaParams P;
+  memset(&P, 0, sizeof(P));
+  P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
+  P.bits = c->bits_dev; P.tscale = c->tscale_dev; P.temps = d_temps.as<double>();
+  P.step0 = a->step0; P.n_steps = a->n_steps; P.seed = a->seed; P.chain_id0 = a->chain_id0;
+  P.proposals = a->proposals ? d_prop.as<int32_t>() : nullptr;
+  P.uniforms = a->uniforms ? d_uni.as<float>() : nullptr;
+  P.accept_out = a->accept_out ? d_acc.as<uint8_t>() : nullptr;
+  P.counters = c->counters_dev;
+  SO_CUDA(cudaEventRecord(c->ev0, c->stream));
+  SO_TRY(so_launch_anneal_analytical(c, P, d_of.as<double>(), c->stream));
+  SO_CUDA(cudaEventRecord(c->ev1, c->stream));
+  if (a->accept_out && ns) SO_CUDA(cudaMemcpyAsync(a->accept_out, d_acc.p, nc * ns, cudaMemcpyDeviceToHost, c->stream));
+  if (of_out) SO_CUDA(cudaMemcpyAsync(of_out, d_of.p, nc * 8, cudaMemcpyDeviceToHost, c->stream));
+  SO_TRY(rescore(c, 0, c->n_chains));               // keep an attached surrogate state consistent with the new bits
+  SO_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) {
+    unsigned long long cnt[3];
+    SO_CUDA(cudaMemcpy(cnt, c->counters_dev, sizeof(cnt), cudaMemcpyDeviceToHost));
+    stats->flips = (int64_t)(nc * ns);
+    stats->accepted = (int64_t)cnt[1];
+    SO_CUDA(cudaEventElapsedTime(&stats->kernel_ms, c->ev0, c->ev1));
+  }
+  return SO_OK;
+}
+
 // ---- best structure / replica exchange -----------------------------------------------------------------------
 int so_best_record_dev(so_chains *c, int64_t chain_id0, void *record_dev, void *stream) {
   SO_REQUIRE(c && record_dev, "NULL argument");

@@ -130,6 +130,10 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_apply_flips(const so_chains *c, int64_t n, const int64_t *chains_dev, const int32_t *sites_dev,
                           cudaStream_t st);
+int so_lsc_max_sites(void);
+int so_launch_lsc_analytical(const so_lattice *lat, const uint32_t *bits_dev, int64_t n, double *site_rates_dev,
+                             double *struct_rate_dev, cudaStream_t st);
+int so_launch_anneal_analytical(const so_chains *c, const SaParams &P, double *of_dev, cudaStream_t st);
 int so_launch_best(const so_chains *c, int64_t chain_id0, void *record_dev, cudaStream_t st);
 int so_launch_exchange(const so_chains *c, int rank, int world, int ladder, int parity, uint64_t seed, int64_t round,
                        double t_ref, const double *of_all, double *tscale_all, double *scratch,

@@ -70,33 +70,13 @@ class LSC_cat(_GraphCat):
     graph_to_KMClattice_V2 = graph_to_KMClattice      # the unfinished upstream variant (OML/LSC_cat.py:114-162)
 
     def eval_struc_rate_anal(self, x):
-        """OML/LSC_cat.py:248-257.  Typing on the GPU; the small dense solve stays on the host for now."""
+        """OML/LSC_cat.py:248-257: analytical structure rate (not normalized) of occupancy x."""
         self.assign_occs(x)
         self.graph_to_KMClattice()
         return np.sum(self.compute_site_rates_lsc())
 
     def compute_site_rates_lsc(self):
-        """OML/LSC_cat.py:260-316 (all rate constants 1)."""
-        kmc_lat = self.KMC_lat
-        n_sites = len(kmc_lat.site_type_inds)
-        site_rates = np.zeros(len(self.variable_occs))
-        if n_sites == 0:
-            return site_rates
-        A = np.zeros([n_sites, n_sites])
-        b = np.zeros(n_sites)
-        A_rate = np.zeros([n_sites, n_sites])
-        for i, t in enumerate(kmc_lat.site_type_inds):
-            if t == 1:
-                A[i, i] += -2.0
-                b[i] += -1.0
-            elif t == 2:
-                A[i, i] += -1.0
-                A_rate[i, i] = 1.0
-        for i, j in kmc_lat.neighbor_list:
-            A[i, i] -= 1.0; A[i, j] += 1.0
-            A[j, j] -= 1.0; A[j, i] += 1.0
-        theta = np.linalg.solve(A, b)
-        kmc_site_rates = A_rate.dot(theta)
-        for i in range(len(kmc_site_rates)):
-            site_rates[self.var_ind_kmc_sites[i]] = kmc_site_rates[i]
-        return site_rates
+        """OML/LSC_cat.py:260-316 (all rate constants 1): typing, assembly of the steady-state system over the typed
+        sites and the dense solve run in one kernel (so_lsc_analytical); rate = coverage on the edge sites."""
+        _, site_rates = self._push().lsc_analytical(0, 1)
+        return site_rates[0]

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "so_anneal": (C.c_int, [C.c_void_p, C.POINTER(AnnealArgs), C.POINTER(AnnealStats)]),
     "so_set_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
     "so_get_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
+    "so_lsc_analytical": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p, c_f64p]),
+    "so_anneal_analytical": (C.c_int, [C.c_void_p, C.POINTER(AnnealArgs), C.POINTER(AnnealStats), c_f64p]),
     "so_best": (C.c_int, [C.c_void_p, c_f64p, c_i64p, c_u32p]),
     "so_best_record_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "so_objectives_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -264,6 +264,33 @@ class Chains(object):
         stats = dict(flips=st.flips, accepted=st.accepted, guard_fired=st.guard_fired, kernel_ms=st.kernel_ms)
         return (stats, acc) if want_accept else stats
 
+    def lsc_analytical(self, chain0=0, n=None, site_rates=True):
+        """(struct_rate[n], site_rates[n, N] or None): analytical steady state of the LSC model for the current bits."""
+        n = self.n - chain0 if n is None else n
+        rate = np.empty(n, dtype=np.float64)
+        sr = np.empty((n, self.lattice.N), dtype=np.float64) if site_rates else None
+        B.check(self.lib.so_lsc_analytical(self.h, chain0, n, _p(sr, B.c_f64p), _p(rate, B.c_f64p)))
+        return rate, sr
+
+    def anneal_analytical(self, temps, step0=0, seed=0, chain_id0=0, proposals=None, uniforms=None, want_accept=False):
+        temps = np.ascontiguousarray(temps, dtype=np.float64)
+        ns = len(temps)
+        a = B.AnnealArgs()
+        a.step0, a.n_steps, a.temps, a.seed, a.chain_id0 = int(step0), ns, _p(temps, B.c_f64p), int(seed), int(chain_id0)
+        if proposals is not None:
+            proposals = np.ascontiguousarray(proposals, dtype=np.int32).reshape(self.n, ns)
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float32).reshape(self.n, ns)
+            a.proposals, a.uniforms = _p(proposals, B.c_i32p), _p(uniforms, B.c_f32p)
+        acc = None
+        if want_accept:
+            acc = np.empty((self.n, ns), dtype=np.uint8)
+            a.accept_out = _p(acc, B.c_u8p)
+        of = np.empty(self.n, dtype=np.float64)
+        st = B.AnnealStats()
+        B.check(self.lib.so_anneal_analytical(self.h, C.byref(a), C.byref(st), _p(of, B.c_f64p)))
+        stats = dict(flips=st.flips, accepted=st.accepted, guard_fired=0, kernel_ms=st.kernel_ms, OF=of)
+        return (stats, acc) if want_accept else stats
+
     def set_tscale(self, tscale, chain0=0):
         tscale = np.ascontiguousarray(tscale, dtype=np.float64).reshape(-1)
         B.check(self.lib.so_set_tscale(self.h, chain0, len(tscale), _p(tscale, B.c_f64p)))

@@ -60,8 +60,10 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
         raise NameError('Unrecognized mode for evaluating objective function')
     temps = cooling_schedule(cooling, T_0, total_steps, py2_linear=py2_linear)
     if mode == 'analytical':
+        if (proposals is None) != (uniforms is None):
+            raise ValueError('proposals and uniforms must be given together')
         return _optimize_analytical(cat, temps, T_0, steps_to_record, step_rec, OF_rec, temps_rec, fldr, prefix,
-                                    proposals, uniforms)
+                                    proposals, uniforms, n_chains=n_chains, seed=seed, return_stats=return_stats)
     if surrogate is None:
         raise NameError('surrogate mode needs a fitted surrogate')
 
@@ -147,37 +149,45 @@ def _save_trajectory(fldr, prefix, step_rec, OF_rec, temps_rec):
 
 
 def _optimize_analytical(cat, temps, T_0, steps_to_record, step_rec, OF_rec, temps_rec, fldr, prefix, proposals,
-                         uniforms):
-    """mode='analytical' (LSC): site typing on the GPU, dense steady-state solve on the host as upstream
-    (OML/LSC_cat.py:248-316).  Not part of the accelerated path."""
-    x = [int(v) for v in cat.variable_occs]
-    OF = cat.eval_struc_rate_anal(x)
+                         uniforms, n_chains=1, seed=None, return_stats=False):
+    """mode='analytical' (LSC, OML/optimize_SA.py:43-44,103-104): every step's objective is the analytical steady
+    state of the toy model, evaluated by so_anneal_analytical (typing + dense solve in shared memory per step)."""
+    x0 = cat._occs_array()
+    N = len(x0)
+    total_steps = len(temps)
+    chains = engine.Chains(cat._lattice, n_chains)
+    chains.set_occupancy(np.repeat(x0[None, :], n_chains, axis=0))
+    if seed is None:
+        seed = random.getrandbits(63)
+    if proposals is not None:
+        proposals = np.ascontiguousarray(proposals, dtype=np.int32).reshape(n_chains, total_steps)
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float32).reshape(n_chains, total_steps)
+    OF, _ = chains.lsc_analytical(site_rates=False)
     record_ind = 0
-    OF_rec[record_ind] = OF / cat.atoms_per_layer
+    OF_rec[record_ind] = OF.max() / cat.atoms_per_layer
     temps_rec[record_ind] = T_0
     record_ind += 1
-    rec = set(int(v) for v in steps_to_record)
-    for step in range(len(temps)):
-        T = temps[step]
-        x_new = [i for i in x]
-        ind = int(proposals[step]) if proposals is not None else random.choice(range(len(x_new)))
-        x_new[ind] = 1 - x_new[ind]
-        OF_new = cat.eval_struc_rate_anal(x_new)
-        delta = OF_new - OF
-        if delta > 0:
-            accept = True
-        elif T > 0:
-            u = float(uniforms[step]) if uniforms is not None else random.random()
-            accept = np.exp(delta / T) > u
-        else:
-            accept = False
-        if accept:
-            x, OF = x_new, OF_new
-        if (step + 1) in rec:
-            step_rec[record_ind] = step + 1
-            OF_rec[record_ind] = OF / cat.atoms_per_layer
-            temps_rec[record_ind] = T
-            record_ind += 1
-    cat.assign_occs(x)
+    stats = dict(flips=0, accepted=0, guard_fired=0, kernel_ms=0.0, seed=seed)
+    done = 0
+    for b in sorted(set(int(v) for v in steps_to_record if v > 0)):
+        seg = slice(done, b)
+        st = chains.anneal_analytical(temps[seg], step0=done, seed=seed,
+                                      proposals=None if proposals is None else proposals[:, seg],
+                                      uniforms=None if uniforms is None else uniforms[:, seg])
+        for k in ('flips', 'accepted', 'kernel_ms'):
+            stats[k] += st[k]
+        OF = st['OF']
+        done = b
+        step_rec[record_ind] = b
+        OF_rec[record_ind] = OF.max() / cat.atoms_per_layer
+        temps_rec[record_ind] = temps[b - 1]
+        record_ind += 1
+    best = int(np.argmax(OF)) if len(OF) else 0
+    x = chains.get_occupancy(best, 1)[0]
+    stats['best_chain'], stats['OF'] = best, float(OF[best])
+    stats['trajectory'] = np.array([step_rec, OF_rec])
+    stats['temperatures'] = temps_rec
+    cat.assign_occs([int(v) for v in x])
+    chains.close()
     _save_trajectory(fldr, prefix, step_rec, OF_rec, temps_rec)
-    return None
+    return stats if return_stats else None

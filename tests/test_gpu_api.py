@@ -245,3 +245,48 @@ def test_database_formats_roundtrip(tmp_path):
     os.makedirs(os.path.join(str(tmp_path), 'unfinished'))
     occs, rates = read_database(folders + [os.path.join(str(tmp_path), 'unfinished')])
     assert occs.shape == (864, 144) and rates.shape == (2, 144)
+
+
+def test_lsc_analytical_batch_matches_oracle():
+    """so_lsc_analytical (typing + dense steady-state solve per structure) vs OML/LSC_cat.py:260-316 restated."""
+    from so_b200 import engine
+    d = 12
+    xs = np.array([LA.make_random_structure(i, 48, d) for i in range(0, 48, 3)] +
+                  [np.zeros(144, np.uint8), np.ones(144, np.uint8)])
+    ch = engine.Chains(engine.Lattice(d, "LSC"), len(xs))
+    ch.set_occupancy(xs)
+    rate, sr = ch.lsc_analytical()
+    for c, x in enumerate(xs):
+        ref = LA.compute_site_rates_lsc(x, d)
+        np.testing.assert_allclose(sr[c], ref, rtol=1e-9, atol=1e-13)       # fp tolerance: 1e-9 relative
+        np.testing.assert_allclose(rate[c], ref.sum(), rtol=1e-9, atol=1e-13)
+    assert rate[-2] == 0.0 and rate[-1] == 0.0                              # no sites / terraces only: no edge flux
+    with pytest.raises(ValueError):
+        engine.Chains(engine.Lattice(16, "LSC"), 1).lsc_analytical()        # 256 sites: beyond the shared-memory solve
+
+
+def test_analytical_sa_matches_oracle():
+    """optimize(mode='analytical') on the device: accept/reject sequence and final occupancy vs the literal loop."""
+    from so_b200 import engine, LSC_cat, optimize
+    d, steps, n = 12, 300, 3
+    rng = np.random.default_rng(4)
+    xs = np.array([LA.make_random_structure(i, 48, d) for i in (5, 17, 30)])
+    prop = rng.integers(0, 144, (n, steps)).astype(np.int32)
+    u = rng.random((n, steps), dtype=np.float32)
+    temps = SA.schedule("exp", 0.05, steps)
+    ch = engine.Chains(engine.Lattice(d, "LSC"), n)
+    ch.set_occupancy(xs)
+    stats, acc = ch.anneal_analytical(temps, proposals=prop, uniforms=u, want_accept=True)
+    for c in range(n):
+        o = SA.optimize_analytical(xs[c], d, temps, prop[c], u[c])
+        safe = o["margin"] > 1e-9                                           # fp64 solves differ in the last bits
+        assert (acc[c].astype(bool)[safe] == o["accept"][safe]).all() and safe.all()
+        assert (ch.get_occupancy(c, 1)[0] == o["x"]).all()
+        np.testing.assert_allclose(stats["OF"][c], o["OF"], rtol=1e-9)
+    # the reference-facing call
+    cat = LSC_cat(d)
+    cat.assign_occs([int(v) for v in xs[0]])
+    out = optimize(cat, mode='analytical', n_cycles=2, T_0=0.05, proposals=prop[0][:288], uniforms=u[0][:288],
+                   n_record=4, return_stats=True)
+    o = SA.optimize_analytical(xs[0], d, SA.schedule("exp", 0.05, 288), prop[0][:288], u[0][:288])
+    assert cat.variable_occs == [int(v) for v in o["x"]] and abs(out["OF"] - o["OF"]) <= 1e-9 * abs(o["OF"])
