@@ -495,6 +495,15 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
       }
   }
   int rc = SO_OK;
+  s->tc_image_dev = nullptr; s->tc_ok = 0;
+  {
+    std::vector<unsigned char> img;
+    int n_mma = 0;
+    if (so_build_tc_image(s, img, &n_mma) == SO_OK) {
+      rc = upload(&s->tc_image_dev, img.data(), img.size());
+      s->tc_ok = (rc == SO_OK);
+    }
+  }
   if (rc == SO_OK) rc = upload(&s->Wst_dev, Wst.data(), (size_t)K * Hp);
   if (rc == SO_OK) rc = upload(&s->offs_dev, s->offs_host.data(), (size_t)K);
   if (rc == SO_OK) rc = upload(&s->W1q_dev, s->W1q_host.data(), (size_t)K * Hp);
@@ -518,7 +527,7 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
 int so_surrogate_destroy(so_surrogate *s) {
   if (!s) return SO_OK;
   cudaSetDevice(s->device);
-  cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
+  cudaFree(s->tc_image_dev); cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
   cudaFree(s->W1d_dev); cudaFree(s->b1d_dev); cudaFree(s->w2d_dev);
   cudaFree(s->t_feature_dev); cudaFree(s->t_thr_dev); cudaFree(s->t_left_dev); cudaFree(s->t_right_dev);
   cudaFree(s->t_active_dev);

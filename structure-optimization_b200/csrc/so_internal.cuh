@@ -43,6 +43,8 @@ struct so_surrogate {
   std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
   int win_ok, win_a1, win_b1, win_a2, win_b2;   // descriptor offsets form the full rectangle [a1,b1] x [a2,b2]
   int32_t *Wst_dev;                             // W1q rows in staged (memory) order of the window
+  unsigned char *tc_image_dev;                  // B operand of the tensor-core scorer (so_score_tc.cu) or NULL
+  int tc_ok;
 };
 
 struct so_chains {
@@ -121,6 +123,9 @@ int so_launch_flip_delta(const so_lattice *lat, const uint32_t *bits_dev, int64_
                          int32_t *d_lsc, int32_t *d_nh3_exp, cudaStream_t st);
 int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
                     long long *hi, long long *lo, int32_t *nact, cudaStream_t st);
+int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, int *n_mma_out);
+int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
+                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st);
 int so_launch_objective(const so_surrogate *s, const long long *hi, const long long *lo, const int32_t *nact, int64_t n,
                         double *of_dev, cudaStream_t st);
 int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_dev, uint8_t *active_dev,

@@ -10,6 +10,7 @@
 // the state streams from HBM (the kernel is bandwidth bound: 4*K*Hp*(1+accept) bytes per flip-evaluation).
 #include "so_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // ---- score: hq, row sums, gate, objective sums; one thread per row -------------------------------------
 template <int HP4>
@@ -515,6 +516,12 @@ static const size_t kSmemTabLimit = 96 * 1024;
 int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
                     long long *hi, long long *lo, int32_t *nact, cudaStream_t st) {
   if (n == 0) return SO_OK;
+  {
+    // rectangular-window surrogates: first layer on the tensor cores (so_score_tc.cu); SO_SCORE_TC=0 keeps the
+    // CUDA-core kernel (both give the same bits; tests compare them)
+    const char *env = getenv("SO_SCORE_TC");
+    if (s->tc_ok && !(env && env[0] == '0')) return so_launch_score_tc(lat, s, bits_dev, n, hq_dev, hi, lo, nact, st);
+  }
   SO_CUDA(cudaMemsetAsync(hi, 0, n * sizeof(long long), st));
   SO_CUDA(cudaMemsetAsync(lo, 0, n * sizeof(long long), st));
   SO_CUDA(cudaMemsetAsync(nact, 0, n * sizeof(int32_t), st));

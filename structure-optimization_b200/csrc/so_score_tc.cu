@@ -1,0 +1,264 @@
+// so_score_tc.cu -- first-layer state + objective of whole structures on the 5th-generation tensor cores (tcgen05).
+//
+// Same result as score_kernel (so_sa.cu), bit for bit: the first layer  hq[r][j] = b1q[j] + sum_k x[r+off_k] W1q[k][j]
+// is an integer GEMM  X[rows x K] (0/1 bytes) * W[K x 4*Hp]  where every int32 weight is split into four BALANCED 8-bit
+// limbs (w = l0 + 2^8 l1 + 2^16 l2 + 2^24 l3, l in [-128,127]); kind::i8 accumulates the limb products exactly in
+// int32 in TMEM and the epilogue recombines them with shifts.  ncu of score_kernel shows it bound by integer issue
+// (980 IMAD per row), which is what makes the contraction pay.
+//
+//   * one CTA (128 threads) walks the 128-row tiles of one chain; a thread owns one lattice site of the tile;
+//   * the descriptor row of a site (rectangular window, <= 8 x 8) is gathered from the chain's bit-plane with one
+//     funnel shift per window row and expanded to bytes through a 256-entry look-up table -> A tile in shared memory
+//     in the canonical K-major no-swizzle layout (8 x 16 B core matrices), 64 K-bytes per row;
+//   * one thread issues 2 x tcgen05.mma (M=128, N=4*Hp, K=32) and commits to an mbarrier; the four warps read their
+//     TMEM lane quarter back with tcgen05.ld, recombine limbs, apply relu . w2q (exact int64) and store the hq row.
+#include "so_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// leading byte offset>>4 [16,30) (between the two 16-B K chunks), stride byte offset>>4 [32,46) (between 8-row
+// groups), version 1 at [46,48), layout type 0 at [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct TcGeom {
+  int a1, a2;        // smallest offsets of the window; K slot p2*8 + p1 <-> site (r1 + a1 + p1, r2 + a2 + p2)
+  int L, n_seg;      // window extent (<= 8 each)
+  int n_mma;         // 4 * Hp, a multiple of 16
+  int b_lbo;         // byte distance between 16-B K chunks of the B image = n_mma * 16
+};
+
+constexpr int TILE_M = 128;
+constexpr int A_LBO = TILE_M * 16;          // 2048 B between 16-B K chunks of the A tile
+constexpr int A_BYTES = 4 * A_LBO;          // 64 K-bytes per row
+
+// L consecutive bits of the chain's bit-plane starting at site (i1s .. i1s+L-1, i2), periodic in i1
+__device__ __forceinline__ uint32_t window_bits(const uint32_t *bits, int d, int i1s, int i2, int L) {
+  auto run = [&](int v0, int n) -> uint32_t {          // n <= 8 bits starting at site index v0
+    uint32_t w0 = bits[v0 >> 5], w1 = bits[(v0 >> 5) + 1];   // (the bit-plane is padded by one word)
+    return __funnelshift_r(w0, w1, v0 & 31) & ((1u << n) - 1u);
+  };
+  if (i1s + L <= d) return run(i2 * d + i1s, L);
+  int n1 = d - i1s;
+  return run(i2 * d + i1s, n1) | (run(i2 * d, L - n1) << n1);
+}
+
+template <int HP4>
+__global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restrict__ bits_all, int d, int N, int W,
+                                                       long long n_chains, SurView sv, TcGeom g,
+                                                       const uint4 *__restrict__ b_image, int32_t *hq_all,
+                                                       long long *hi_out, long long *lo_out, int32_t *nact_out) {
+  constexpr int HP = HP4 * 4;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  unsigned char *s_A = s_raw;                                   // [4 chunks][16 groups][8 rows][16 B]
+  unsigned char *s_B = s_A + A_BYTES;                           // [4 chunks][n_mma/8 groups][8][16 B]
+  uint2 *s_lut = (uint2 *)(s_B + 4 * g.b_lbo);                  // 256 x 8 B: bit pattern -> bytes
+  uint32_t *s_bits = (uint32_t *)(s_lut + 256);                 // W + 1 words
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ long long s_hi, s_lo;
+  __shared__ int s_n;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int i = tid; i < (4 * g.b_lbo) / 16; i += blockDim.x) ((uint4 *)s_B)[i] = b_image[i];
+  for (int i = tid; i < 256; i += blockDim.x) {
+    uint32_t lo = 0, hi = 0;
+    for (int b = 0; b < 4; ++b) { lo |= ((i >> b) & 1u) << (8 * b); hi |= ((i >> (b + 4)) & 1u) << (8 * b); }
+    s_lut[i] = make_uint2(lo, hi);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {                                             // 128 accumulator columns (n_mma <= 128 here)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32 [4,6)=2, A = u8 [7,10)=0, B = s8 [10,13)=1,
+  // both K-major, N>>3 at [17,23), M>>4 at [24,29)
+  const uint32_t idesc = (2u << 4) | (1u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  const uint32_t a_addr = smem_u32(s_A), b_addr = smem_u32(s_B), bar = smem_u32(&s_bar);
+  uint32_t parity = 0;
+  const int n_tiles = (N + TILE_M - 1) / TILE_M;
+  int b1q[HP], w2q[HP];
+#pragma unroll
+  for (int j = 0; j < HP; ++j) { b1q[j] = __ldg(sv.b1q + j); w2q[j] = __ldg(sv.w2q + j); }
+
+  for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
+    __syncthreads();
+    for (int w = tid; w <= W; w += blockDim.x) s_bits[w] = w < W ? bits_all[c * W + w] : 0u;
+    if (tid == 0) { s_hi = 0; s_lo = 0; s_n = 0; }
+    __syncthreads();
+    long long my_hi = 0, my_lo = 0;
+    int my_n = 0;
+    BitView bv{s_bits, d, -1};
+    for (int t = 0; t < n_tiles; ++t) {
+      const int r = t * TILE_M + tid;
+      // ---- A tile: this thread's descriptor row, 8 K-bytes per window row ----------------------------------------
+      {
+        uint2 seg[8];
+#pragma unroll
+        for (int p2 = 0; p2 < 8; ++p2) seg[p2] = make_uint2(0u, 0u);
+        if (r < N) {
+          const int r2 = r / d, r1 = r - r2 * d;
+          const int i1s = wrap(r1 + g.a1, d);
+#pragma unroll
+          for (int p2 = 0; p2 < 8; ++p2)
+            if (p2 < g.n_seg) seg[p2] = s_lut[window_bits(s_bits, d, i1s, wrap(r2 + g.a2 + p2, d), g.L)];
+        }
+        unsigned char *row = s_A + (tid >> 3) * 128 + (tid & 7) * 16;
+#pragma unroll
+        for (int ck = 0; ck < 4; ++ck)
+          *(uint4 *)(row + ck * A_LBO) = make_uint4(seg[2 * ck].x, seg[2 * ck].y, seg[2 * ck + 1].x, seg[2 * ck + 1].y);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mma_i8(tmem, umma_desc(a_addr, A_LBO, 128), umma_desc(b_addr, g.b_lbo, 128), idesc, 0u);
+        mma_i8(tmem, umma_desc(a_addr + 2 * A_LBO, A_LBO, 128), umma_desc(b_addr + 2 * g.b_lbo, g.b_lbo, 128), idesc, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      }
+      {
+        uint32_t ok;
+        do {
+          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        } while (!ok);
+        parity ^= 1u;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- epilogue: TMEM lane = tile row; columns n = 4*j + limb -------------------------------------------------
+      {
+        int h[HP];
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int q = 0; q < HP4; ++q) {
+          int v[16];
+          tmem_ld16(lane_base + q * 16, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * q + jj;
+            h[j] = b1q[j] + v[4 * jj] + v[4 * jj + 1] * 256 + v[4 * jj + 2] * 65536 + (int)((unsigned)v[4 * jj + 3] << 24);
+          }
+        }
+        if (r < N) {
+          long long A = 0;
+#pragma unroll
+          for (int j = 0; j < HP; ++j) A += (long long)w2q[j] * (long long)max(h[j], 0);
+          if (hq_all) {
+            int4 *dst = (int4 *)(hq_all + ((size_t)c * N + r) * HP);
+#pragma unroll
+            for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
+          }
+          const int r2 = r / d, r1 = r - r2 * d;
+          const int gate = sv.gated ? tree_gate(sv, bv, r1, r2) : 1;
+          if (gate) { my_hi += A >> SO_SPLIT_BITS; my_lo += A & SO_SPLIT_MASK; ++my_n; }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMA
+    }
+    my_hi = warp_sum_ll(my_hi);
+    my_lo = warp_sum_ll(my_lo);
+    my_n = warp_sum_i(my_n);
+    if ((tid & 31) == 0) {
+      atomicAdd((unsigned long long *)&s_hi, (unsigned long long)my_hi);
+      atomicAdd((unsigned long long *)&s_lo, (unsigned long long)my_lo);
+      atomicAdd(&s_n, my_n);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long l = s_lo;
+      hi_out[c] = s_hi + (l >> SO_SPLIT_BITS);
+      lo_out[c] = l & SO_SPLIT_MASK;
+      nact_out[c] = s_n;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace
+
+// host: the B operand image (balanced 8-bit limbs of W1q in the canonical K-major layout) for a window surrogate.
+// K slot s = p2*8 + p1 holds descriptor column k with offset (a1+p1, a2+p2); column n = 4*j + limb.
+int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, int *n_mma_out) {
+  const int Hp = s->Hp, n_mma = 4 * Hp;
+  const int L = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
+  if (!s->win_ok || L > 8 || nseg > 8 || n_mma > 128 || (n_mma % 16) != 0) return SO_EINVAL;
+  const int b_lbo = n_mma * 16;
+  img.assign((size_t)4 * b_lbo, 0);
+  for (int k = 0; k < s->K; ++k) {
+    int o1 = (int)(short)(s->offs_host[k] & 0xffff), o2 = s->offs_host[k] >> 16;
+    int slot = (o2 - s->win_a2) * 8 + (o1 - s->win_a1);
+    for (int j = 0; j < Hp; ++j) {
+      long long w = s->W1q_host[(size_t)k * Hp + j];
+      for (int l = 0; l < 4; ++l) {
+        long long limb = l < 3 ? (((w + 128) & 255) - 128) : w;      // balanced digit; the top limb keeps the sign
+        w = (w - limb) >> 8;
+        if (l == 3 && (limb < -128 || limb > 127)) return SO_EINVAL;
+        int n = 4 * j + l;
+        img[(size_t)(slot >> 4) * b_lbo + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16 + (slot & 15)] = (unsigned char)(signed char)limb;
+      }
+    }
+  }
+  *n_mma_out = n_mma;
+  return SO_OK;
+}
+
+int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
+                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st) {
+  if (n == 0) return SO_OK;
+  TcGeom g;
+  g.a1 = s->win_a1; g.a2 = s->win_a2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
+  g.n_mma = 4 * s->Hp; g.b_lbo = g.n_mma * 16;
+  size_t smem = (size_t)A_BYTES + (size_t)4 * g.b_lbo + 256 * 8 + ((size_t)lat->W + 1) * 4 + 64;
+  int n_sm = 0;
+  SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, lat->device));
+  int blocks = (int)(n < (int64_t)n_sm * 4 ? n : (int64_t)n_sm * 4);     // 4 CTAs x 128 TMEM columns per SM
+  SurView sv = make_view(s);
+  switch (s->HP4) {
+#define SO_TC_CASE(V)                                                                                              \
+  case V: {                                                                                                        \
+    auto kern = score_tc_kernel<V>;                                                                                \
+    SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+    kern<<<blocks, 128, smem, st>>>(bits_dev, lat->d, lat->N, lat->W, n, sv, g, (const uint4 *)s->tc_image_dev,    \
+                                    hq_dev, hi, lo, nact);                                                         \
+  } break;
+    SO_TC_CASE(1) SO_TC_CASE(2) SO_TC_CASE(3) SO_TC_CASE(4) SO_TC_CASE(5) SO_TC_CASE(6) SO_TC_CASE(7) SO_TC_CASE(8)
+#undef SO_TC_CASE
+    default: so_set_error("hidden width not supported by the tensor-core scorer"); return SO_EINVAL;
+  }
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
