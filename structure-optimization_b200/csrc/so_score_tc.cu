@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
   unsigned char *s_A = s_raw;                                   // [4 chunks][16 groups][8 rows][16 B]
   unsigned char *s_B = s_A + A_BYTES;                           // [4 chunks][n_mma/8 groups][8][16 B]
   uint2 *s_lut = (uint2 *)(s_B + 4 * g.b_lbo);                  // 256 x 8 B: bit pattern -> bytes
-  uint32_t *s_bits = (uint32_t *)(s_lut + 256);                 // W + 1 words
+  int4 *s_out = (int4 *)(s_lut + 256);                          // 2 x [128 rows][HP4 int4]: hq tile staged for a bulk store
+  uint32_t *s_bits = (uint32_t *)(s_out + 2 * TILE_M * HP4);    // W + 1 words
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
   __shared__ long long s_hi, s_lo;
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
           long long A = 0;
 #pragma unroll
           for (int j = 0; j < HP; ++j) A += (long long)w2q[j] * (long long)max(h[j], 0);
-          if (hq_all) {
-            int4 *dst = (int4 *)(hq_all + ((size_t)c * N + r) * HP);
+          if (hq_all) {                                 // 80-B row stride: conflict-free 16-B shared stores
+            int4 *dst = s_out + (size_t)(t & 1) * TILE_M * HP4 + (size_t)tid * HP4;
 #pragma unroll
             for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
           }
@@ -187,7 +188,22 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMA
+      if (hq_all) {
+        // the tile's rows are contiguous in hq: one bulk-async store of up to 128*4*HP bytes, double buffered
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+          const int rows = min(TILE_M, N - t * TILE_M);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                           hq_all + ((size_t)c * N + (size_t)t * TILE_M) * HP),
+                       "r"(smem_u32(s_out + (size_t)(t & 1) * TILE_M * HP4)), "r"((uint32_t)(rows * HP * 4))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the other buffer is free again
+        }
+      }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     my_hi = warp_sum_ll(my_hi);
     my_lo = warp_sum_ll(my_lo);
     my_n = warp_sum_i(my_n);
@@ -242,7 +258,7 @@ int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint3
   TcGeom g;
   g.a1 = s->win_a1; g.a2 = s->win_a2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
   g.n_mma = 4 * s->Hp; g.b_lbo = g.n_mma * 16;
-  size_t smem = (size_t)A_BYTES + (size_t)4 * g.b_lbo + 256 * 8 + ((size_t)lat->W + 1) * 4 + 64;
+  size_t smem = (size_t)A_BYTES + (size_t)4 * g.b_lbo + 256 * 8 + (size_t)2 * TILE_M * s->Hp * 4 + ((size_t)lat->W + 1) * 4 + 64;
   int n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, lat->device));
   int blocks = (int)(n < (int64_t)n_sm * 4 ? n : (int64_t)n_sm * 4);     // 4 CTAs x 128 TMEM columns per SM
