@@ -123,6 +123,7 @@ int so_launch_flip_delta(const so_lattice *lat, const uint32_t *bits_dev, int64_
                          int32_t *d_lsc, int32_t *d_nh3_exp, cudaStream_t st);
 int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
                     long long *hi, long long *lo, int32_t *nact, cudaStream_t st);
+int so_normalize_sums(long long *hi, long long *lo, int64_t n, cudaStream_t st);
 int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, int *n_mma_out);
 int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
                        long long *hi, long long *lo, int32_t *nact, cudaStream_t st);

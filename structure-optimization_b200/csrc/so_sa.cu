@@ -549,6 +549,13 @@ int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t
   return SO_OK;
 }
 
+int so_normalize_sums(long long *hi, long long *lo, int64_t n, cudaStream_t st) {
+  if (n == 0) return SO_OK;
+  normalize_sums_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hi, lo, n);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+
 int so_launch_objective(const so_surrogate *s, const long long *hi, const long long *lo, const int32_t *nact, int64_t n,
                         double *of_dev, cudaStream_t st) {
   if (n == 0) return SO_OK;

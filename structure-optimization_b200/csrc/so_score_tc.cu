@@ -46,19 +46,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
 }
 
 struct TcGeom {
-  int a1, a2;        // smallest offsets of the window; K slot p2*8 + p1 <-> site (r1 + a1 + p1, r2 + a2 + p2)
-  int L, n_seg;      // window extent (<= 8 each)
+  int a1, a2;        // smallest offsets of the window; K slot p2*KW + p1 <-> site (r1 + a1 + p1, r2 + a2 + p2)
+  int L, n_seg;      // window extent (<= 16 each)
+  int kw;            // K bytes per window row: 8 (L <= 8) or 16
+  int n_chunks;      // 16-B K chunks per row (even: one MMA consumes two)
   int n_mma;         // 4 * Hp, a multiple of 16
   int b_lbo;         // byte distance between 16-B K chunks of the B image = n_mma * 16
 };
 
 constexpr int TILE_M = 128;
 constexpr int A_LBO = TILE_M * 16;          // 2048 B between 16-B K chunks of the A tile
-constexpr int A_BYTES = 4 * A_LBO;          // 64 K-bytes per row
 
-// L consecutive bits of the chain's bit-plane starting at site (i1s .. i1s+L-1, i2), periodic in i1
+// L (<= 16) consecutive bits of a bit-plane starting at site (i1s .. i1s+L-1, i2), periodic in i1
 __device__ __forceinline__ uint32_t window_bits(const uint32_t *bits, int d, int i1s, int i2, int L) {
-  auto run = [&](int v0, int n) -> uint32_t {          // n <= 8 bits starting at site index v0
+  auto run = [&](int v0, int n) -> uint32_t {          // n <= 16 bits starting at site index v0
     uint32_t w0 = bits[v0 >> 5], w1 = bits[(v0 >> 5) + 1];   // (the bit-plane is padded by one word)
     return __funnelshift_r(w0, w1, v0 & 31) & ((1u << n) - 1u);
   };
@@ -67,6 +68,8 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t *bits, int d, int
   return run(i2 * d + i1s, n1) | (run(i2 * d, L - n1) << n1);
 }
 
+// Rows are the concatenation (chain, site): global row G = chain * N + site; a CTA owns a contiguous range of
+// 128-row tiles, so a tile touches at most two chains (N >= 128) whose bit-planes sit in two shared-memory slots.
 template <int HP4>
 __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restrict__ bits_all, int d, int N, int W,
                                                        long long n_chains, SurView sv, TcGeom g,
@@ -74,18 +77,16 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
                                                        long long *hi_out, long long *lo_out, int32_t *nact_out) {
   constexpr int HP = HP4 * 4;
   extern __shared__ __align__(128) unsigned char s_raw[];
-  unsigned char *s_A = s_raw;                                   // [4 chunks][16 groups][8 rows][16 B]
-  unsigned char *s_B = s_A + A_BYTES;                           // [4 chunks][n_mma/8 groups][8][16 B]
-  uint2 *s_lut = (uint2 *)(s_B + 4 * g.b_lbo);                  // 256 x 8 B: bit pattern -> bytes
+  unsigned char *s_A = s_raw;                                   // [n_chunks][16 groups][8 rows][16 B]
+  unsigned char *s_B = s_A + g.n_chunks * A_LBO;                // [n_chunks][n_mma/8 groups][8][16 B]
+  uint2 *s_lut = (uint2 *)(s_B + g.n_chunks * g.b_lbo);         // 256 x 8 B: bit pattern -> bytes
   int4 *s_out = (int4 *)(s_lut + 256);                          // 2 x [128 rows][HP4 int4]: hq tile staged for a bulk store
-  uint32_t *s_bits = (uint32_t *)(s_out + 2 * TILE_M * HP4);    // W + 1 words
+  uint32_t *s_bits = (uint32_t *)(s_out + 2 * TILE_M * HP4);    // 2 slots x (W + 1) words
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
-  __shared__ long long s_hi, s_lo;
-  __shared__ int s_n;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < (4 * g.b_lbo) / 16; i += blockDim.x) ((uint4 *)s_B)[i] = b_image[i];
+  for (int i = tid; i < (g.n_chunks * g.b_lbo) / 16; i += blockDim.x) ((uint4 *)s_B)[i] = b_image[i];
   for (int i = tid; i < 256; i += blockDim.x) {
     uint32_t lo = 0, hi = 0;
     for (int b = 0; b < 4; ++b) { lo |= ((i >> b) & 1u) << (8 * b); hi |= ((i >> (b + 4)) & 1u) << (8 * b); }
@@ -108,118 +109,137 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
   const uint32_t idesc = (2u << 4) | (1u << 10) | ((uint32_t)(g.n_mma >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   const uint32_t a_addr = smem_u32(s_A), b_addr = smem_u32(s_B), bar = smem_u32(&s_bar);
   uint32_t parity = 0;
-  const int n_tiles = (N + TILE_M - 1) / TILE_M;
   int b1q[HP], w2q[HP];
 #pragma unroll
   for (int j = 0; j < HP; ++j) { b1q[j] = __ldg(sv.b1q + j); w2q[j] = __ldg(sv.w2q + j); }
 
-  for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
-    __syncthreads();
-    for (int w = tid; w <= W; w += blockDim.x) s_bits[w] = w < W ? bits_all[c * W + w] : 0u;
-    if (tid == 0) { s_hi = 0; s_lo = 0; s_n = 0; }
-    __syncthreads();
-    long long my_hi = 0, my_lo = 0;
-    int my_n = 0;
-    BitView bv{s_bits, d, -1};
-    for (int t = 0; t < n_tiles; ++t) {
-      const int r = t * TILE_M + tid;
-      // ---- A tile: this thread's descriptor row, 8 K-bytes per window row ----------------------------------------
-      {
-        uint2 seg[8];
-#pragma unroll
-        for (int p2 = 0; p2 < 8; ++p2) seg[p2] = make_uint2(0u, 0u);
-        if (r < N) {
-          const int r2 = r / d, r1 = r - r2 * d;
-          const int i1s = wrap(r1 + g.a1, d);
-#pragma unroll
-          for (int p2 = 0; p2 < 8; ++p2)
-            if (p2 < g.n_seg) seg[p2] = s_lut[window_bits(s_bits, d, i1s, wrap(r2 + g.a2 + p2, d), g.L)];
-        }
-        unsigned char *row = s_A + (tid >> 3) * 128 + (tid & 7) * 16;
-#pragma unroll
-        for (int ck = 0; ck < 4; ++ck)
-          *(uint4 *)(row + ck * A_LBO) = make_uint4(seg[2 * ck].x, seg[2 * ck].y, seg[2 * ck + 1].x, seg[2 * ck + 1].y);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  const long long total_rows = n_chains * (long long)N;
+  const long long n_tiles = (total_rows + TILE_M - 1) / TILE_M;
+  const long long per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = blockIdx.x * per_cta, t_end = min(n_tiles, t_begin + per_cta);
+  long long slot_chain = -1;                        // chain whose bit-plane is in slot 0 (slot 1 = the next chain)
+  int buf = 0;
+
+  for (long long t = t_begin; t < t_end; ++t) {
+    const long long G0 = t * TILE_M, G = G0 + tid;
+    const long long c0 = G0 / N;
+    if (c0 != slot_chain) {                         // (re)load the two bit-planes this and the following tiles need
       __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        mma_i8(tmem, umma_desc(a_addr, A_LBO, 128), umma_desc(b_addr, g.b_lbo, 128), idesc, 0u);
-        mma_i8(tmem, umma_desc(a_addr + 2 * A_LBO, A_LBO, 128), umma_desc(b_addr + 2 * g.b_lbo, g.b_lbo, 128), idesc, 1u);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      for (int w = tid; w < 2 * (W + 1); w += blockDim.x) {
+        int sl = w / (W + 1), ww = w - sl * (W + 1);
+        long long cc = c0 + sl;
+        s_bits[w] = (ww < W && cc < n_chains) ? bits_all[cc * W + ww] : 0u;
       }
-      {
-        uint32_t ok;
-        do {
-          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        } while (!ok);
-        parity ^= 1u;
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- epilogue: TMEM lane = tile row; columns n = 4*j + limb -------------------------------------------------
-      {
-        int h[HP];
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-        for (int q = 0; q < HP4; ++q) {
-          int v[16];
-          tmem_ld16(lane_base + q * 16, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * q + jj;
-            h[j] = b1q[j] + v[4 * jj] + v[4 * jj + 1] * 256 + v[4 * jj + 2] * 65536 + (int)((unsigned)v[4 * jj + 3] << 24);
-          }
+      slot_chain = c0;
+      __syncthreads();
+    }
+    const bool live = G < total_rows;
+    const long long c = live ? G / N : c0;
+    const int r = live ? (int)(G - c * N) : 0;
+    const int r2 = r / d, r1 = r - r2 * d;
+    const uint32_t *mybits = s_bits + (size_t)(c - c0) * (W + 1);
+    // ---- A tile: this thread's descriptor row, kw K-bytes per window row -------------------------------------------
+    {
+      unsigned char *row = s_A + (tid >> 3) * 128 + (tid & 7) * 16;
+      const int i1s = wrap(r1 + g.a1, d);
+      if (g.kw == 8) {
+        for (int ck = 0; ck < g.n_chunks; ++ck) {
+          uint2 s0 = make_uint2(0u, 0u), s1 = make_uint2(0u, 0u);
+          if (live && 2 * ck < g.n_seg) s0 = s_lut[window_bits(mybits, d, i1s, wrap(r2 + g.a2 + 2 * ck, d), g.L)];
+          if (live && 2 * ck + 1 < g.n_seg) s1 = s_lut[window_bits(mybits, d, i1s, wrap(r2 + g.a2 + 2 * ck + 1, d), g.L)];
+          *(uint4 *)(row + ck * A_LBO) = make_uint4(s0.x, s0.y, s1.x, s1.y);
         }
-        if (r < N) {
-          long long A = 0;
-#pragma unroll
-          for (int j = 0; j < HP; ++j) A += (long long)w2q[j] * (long long)max(h[j], 0);
-          if (hq_all) {                                 // 80-B row stride: conflict-free 16-B shared stores
-            int4 *dst = s_out + (size_t)(t & 1) * TILE_M * HP4 + (size_t)tid * HP4;
-#pragma unroll
-            for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
+      } else {
+        for (int ck = 0; ck < g.n_chunks; ++ck) {
+          uint2 s0 = make_uint2(0u, 0u), s1 = make_uint2(0u, 0u);
+          if (live && ck < g.n_seg) {
+            uint32_t pat = window_bits(mybits, d, i1s, wrap(r2 + g.a2 + ck, d), g.L);
+            s0 = s_lut[pat & 255u];
+            s1 = s_lut[pat >> 8];
           }
-          const int r2 = r / d, r1 = r - r2 * d;
-          const int gate = sv.gated ? tree_gate(sv, bv, r1, r2) : 1;
-          if (gate) { my_hi += A >> SO_SPLIT_BITS; my_lo += A & SO_SPLIT_MASK; ++my_n; }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMA
-      if (hq_all) {
-        // the tile's rows are contiguous in hq: one bulk-async store of up to 128*4*HP bytes, double buffered
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-          const int rows = min(TILE_M, N - t * TILE_M);
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                           hq_all + ((size_t)c * N + (size_t)t * TILE_M) * HP),
-                       "r"(smem_u32(s_out + (size_t)(t & 1) * TILE_M * HP4)), "r"((uint32_t)(rows * HP * 4))
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the other buffer is free again
+          *(uint4 *)(row + ck * A_LBO) = make_uint4(s0.x, s0.y, s1.x, s1.y);
         }
       }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    my_hi = warp_sum_ll(my_hi);
-    my_lo = warp_sum_ll(my_lo);
-    my_n = warp_sum_i(my_n);
-    if ((tid & 31) == 0) {
-      atomicAdd((unsigned long long *)&s_hi, (unsigned long long)my_hi);
-      atomicAdd((unsigned long long *)&s_lo, (unsigned long long)my_lo);
-      atomicAdd(&s_n, my_n);
-    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
-      long long l = s_lo;
-      hi_out[c] = s_hi + (l >> SO_SPLIT_BITS);
-      lo_out[c] = l & SO_SPLIT_MASK;
-      nact_out[c] = s_n;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kk = 0; kk < g.n_chunks; kk += 2)
+        mma_i8(tmem, umma_desc(a_addr + kk * A_LBO, A_LBO, 128), umma_desc(b_addr + kk * g.b_lbo, g.b_lbo, 128), idesc,
+               kk > 0 ? 1u : 0u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    {
+      uint32_t ok;
+      do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      } while (!ok);
+      parity ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: TMEM lane = tile row; columns n = 4*j + limb ---------------------------------------------------
+    long long my_hi = 0, my_lo = 0;
+    int my_n = 0;
+    {
+      int h[HP];
+      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int q = 0; q < HP4; ++q) {
+        int v[16];
+        tmem_ld16(lane_base + q * 16, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * q + jj;
+          h[j] = b1q[j] + v[4 * jj] + v[4 * jj + 1] * 256 + v[4 * jj + 2] * 65536 + (int)((unsigned)v[4 * jj + 3] << 24);
+        }
+      }
+      if (live) {
+        long long A = 0;
+#pragma unroll
+        for (int j = 0; j < HP; ++j) A += (long long)w2q[j] * (long long)max(h[j], 0);
+        if (hq_all) {                                 // 80-B row stride: conflict-free 16-B shared stores
+          int4 *dst = s_out + (size_t)buf * TILE_M * HP4 + (size_t)tid * HP4;
+#pragma unroll
+          for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
+        }
+        BitView bv{mybits, d, -1};
+        const int gate = sv.gated ? tree_gate(sv, bv, r1, r2) : 1;
+        if (gate) { my_hi = A >> SO_SPLIT_BITS; my_lo = A & SO_SPLIT_MASK; my_n = 1; }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMA
+    // objective sums: a tile touches chains c0 and c0 + 1; exact integer atomics, normalised by the caller
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const bool mine = live && (c - c0) == sl;
+      long long shi = warp_sum_ll(mine ? my_hi : 0), slo = warp_sum_ll(mine ? my_lo : 0);
+      int sn = warp_sum_i(mine ? my_n : 0);
+      if (lane == 0 && (shi | slo | sn) != 0 && c0 + sl < n_chains) {
+        atomicAdd((unsigned long long *)(hi_out + c0 + sl), (unsigned long long)shi);
+        atomicAdd((unsigned long long *)(lo_out + c0 + sl), (unsigned long long)slo);
+        atomicAdd(nact_out + c0 + sl, sn);
+      }
+    }
+    if (hq_all) {
+      // the tile's rows are contiguous in hq: one bulk-async store of up to 128*4*HP bytes, double buffered
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        const int rows = (int)min((long long)TILE_M, total_rows - G0);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(hq_all + (size_t)G0 * HP),
+                     "r"(smem_u32(s_out + (size_t)buf * TILE_M * HP4)), "r"((uint32_t)(rows * HP * 4))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the other buffer is free again
+      }
+      buf ^= 1;
     }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
 }
@@ -227,16 +247,18 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
 }  // namespace
 
 // host: the B operand image (balanced 8-bit limbs of W1q in the canonical K-major layout) for a window surrogate.
-// K slot s = p2*8 + p1 holds descriptor column k with offset (a1+p1, a2+p2); column n = 4*j + limb.
+// K slot s = p2*kw + p1 holds descriptor column k with offset (a1+p1, a2+p2); column n = 4*j + limb.
 int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, int *n_mma_out) {
   const int Hp = s->Hp, n_mma = 4 * Hp;
   const int L = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
-  if (!s->win_ok || L > 8 || nseg > 8 || n_mma > 128 || (n_mma % 16) != 0) return SO_EINVAL;
+  if (!s->win_ok || L > 16 || nseg > 16 || n_mma > 128 || (n_mma % 16) != 0 || s->lat->N < TILE_M) return SO_EINVAL;
+  const int kw = L <= 8 ? 8 : 16;
+  const int n_chunks = ((nseg * kw + 31) / 32) * 2;
   const int b_lbo = n_mma * 16;
-  img.assign((size_t)4 * b_lbo, 0);
+  img.assign((size_t)n_chunks * b_lbo, 0);
   for (int k = 0; k < s->K; ++k) {
     int o1 = (int)(short)(s->offs_host[k] & 0xffff), o2 = s->offs_host[k] >> 16;
-    int slot = (o2 - s->win_a2) * 8 + (o1 - s->win_a1);
+    int slot = (o2 - s->win_a2) * kw + (o1 - s->win_a1);
     for (int j = 0; j < Hp; ++j) {
       long long w = s->W1q_host[(size_t)k * Hp + j];
       for (int l = 0; l < 4; ++l) {
@@ -257,11 +279,18 @@ int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint3
   if (n == 0) return SO_OK;
   TcGeom g;
   g.a1 = s->win_a1; g.a2 = s->win_a2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
+  g.kw = g.L <= 8 ? 8 : 16;
+  g.n_chunks = ((g.n_seg * g.kw + 31) / 32) * 2;
   g.n_mma = 4 * s->Hp; g.b_lbo = g.n_mma * 16;
-  size_t smem = (size_t)A_BYTES + (size_t)4 * g.b_lbo + 256 * 8 + (size_t)2 * TILE_M * s->Hp * 4 + ((size_t)lat->W + 1) * 4 + 64;
+  SO_CUDA(cudaMemsetAsync(hi, 0, n * sizeof(long long), st));
+  SO_CUDA(cudaMemsetAsync(lo, 0, n * sizeof(long long), st));
+  SO_CUDA(cudaMemsetAsync(nact, 0, n * sizeof(int32_t), st));
+  size_t smem = (size_t)g.n_chunks * A_LBO + (size_t)g.n_chunks * g.b_lbo + 256 * 8 + (size_t)2 * TILE_M * s->Hp * 4 +
+                (size_t)2 * (lat->W + 1) * 4 + 64;
   int n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, lat->device));
-  int blocks = (int)(n < (int64_t)n_sm * 4 ? n : (int64_t)n_sm * 4);     // 4 CTAs x 128 TMEM columns per SM
+  long long tiles = (n * (long long)lat->N + TILE_M - 1) / TILE_M;
+  int blocks = (int)(tiles < (long long)n_sm * 4 ? tiles : (long long)n_sm * 4);     // 4 CTAs x 128 TMEM columns per SM
   SurView sv = make_view(s);
   switch (s->HP4) {
 #define SO_TC_CASE(V)                                                                                              \
@@ -276,5 +305,5 @@ int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint3
     default: so_set_error("hidden width not supported by the tensor-core scorer"); return SO_EINVAL;
   }
   SO_CUDA(cudaGetLastError());
-  return SO_OK;
+  return so_normalize_sums(hi, lo, n, st);
 }
