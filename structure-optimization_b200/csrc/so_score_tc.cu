@@ -70,23 +70,26 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t *bits, int d, int
 
 // Rows are the concatenation (chain, site): global row G = chain * N + site; a CTA owns a contiguous range of
 // 128-row tiles, so a tile touches at most two chains (N >= 128) whose bit-planes sit in two shared-memory slots.
-template <int HP4>
+// NCH = 16-B K chunks per row at compile time (4 = the <= 8 x 8 window case, loops fully unrolled) or 0 = runtime.
+template <int HP4, int NCH>
 __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restrict__ bits_all, int d, int N, int W,
                                                        long long n_chains, SurView sv, TcGeom g,
                                                        const uint4 *__restrict__ b_image, int32_t *hq_all,
                                                        long long *hi_out, long long *lo_out, int32_t *nact_out) {
   constexpr int HP = HP4 * 4;
+  const int n_chunks = NCH ? NCH : g.n_chunks;
+  const bool kw8 = NCH ? true : (g.kw == 8);
   extern __shared__ __align__(128) unsigned char s_raw[];
   unsigned char *s_A = s_raw;                                   // [n_chunks][16 groups][8 rows][16 B]
-  unsigned char *s_B = s_A + g.n_chunks * A_LBO;                // [n_chunks][n_mma/8 groups][8][16 B]
-  uint2 *s_lut = (uint2 *)(s_B + g.n_chunks * g.b_lbo);         // 256 x 8 B: bit pattern -> bytes
+  unsigned char *s_B = s_A + n_chunks * A_LBO;                  // [n_chunks][n_mma/8 groups][8][16 B]
+  uint2 *s_lut = (uint2 *)(s_B + n_chunks * g.b_lbo);           // 256 x 8 B: bit pattern -> bytes
   int4 *s_out = (int4 *)(s_lut + 256);                          // 2 x [128 rows][HP4 int4]: hq tile staged for a bulk store
   uint32_t *s_bits = (uint32_t *)(s_out + 2 * TILE_M * HP4);    // 2 slots x (W + 1) words
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < (g.n_chunks * g.b_lbo) / 16; i += blockDim.x) ((uint4 *)s_B)[i] = b_image[i];
+  for (int i = tid; i < (n_chunks * g.b_lbo) / 16; i += blockDim.x) ((uint4 *)s_B)[i] = b_image[i];
   for (int i = tid; i < 256; i += blockDim.x) {
     uint32_t lo = 0, hi = 0;
     for (int b = 0; b < 4; ++b) { lo |= ((i >> b) & 1u) << (8 * b); hi |= ((i >> (b + 4)) & 1u) << (8 * b); }
@@ -119,10 +122,11 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
   const long long t_begin = blockIdx.x * per_cta, t_end = min(n_tiles, t_begin + per_cta);
   long long slot_chain = -1;                        // chain whose bit-plane is in slot 0 (slot 1 = the next chain)
   int buf = 0;
+  long long c0 = (t_begin * TILE_M) / N;            // chain and site of the first row of the current tile,
+  int r0 = (int)(t_begin * TILE_M - c0 * N);        // advanced incrementally (N >= 128: at most one wrap per tile)
 
   for (long long t = t_begin; t < t_end; ++t) {
     const long long G0 = t * TILE_M, G = G0 + tid;
-    const long long c0 = G0 / N;
     if (c0 != slot_chain) {                         // (re)load the two bit-planes this and the following tiles need
       __syncthreads();
       for (int w = tid; w < 2 * (W + 1); w += blockDim.x) {
@@ -134,16 +138,19 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
       __syncthreads();
     }
     const bool live = G < total_rows;
-    const long long c = live ? G / N : c0;
-    const int r = live ? (int)(G - c * N) : 0;
+    const int rr = r0 + tid;
+    const int sl_mine = (live && rr >= N) ? 1 : 0;  // 0: chain c0, 1: chain c0 + 1
+    const int r = live ? (sl_mine ? rr - N : rr) : 0;
     const int r2 = r / d, r1 = r - r2 * d;
-    const uint32_t *mybits = s_bits + (size_t)(c - c0) * (W + 1);
+    const uint32_t *mybits = s_bits + (size_t)sl_mine * (W + 1);
     // ---- A tile: this thread's descriptor row, kw K-bytes per window row -------------------------------------------
     {
       unsigned char *row = s_A + (tid >> 3) * 128 + (tid & 7) * 16;
       const int i1s = wrap(r1 + g.a1, d);
-      if (g.kw == 8) {
-        for (int ck = 0; ck < g.n_chunks; ++ck) {
+      if (kw8) {
+#pragma unroll
+        for (int ck = 0; ck < (NCH ? NCH : 16); ++ck) {
+          if (ck >= n_chunks) break;
           uint2 s0 = make_uint2(0u, 0u), s1 = make_uint2(0u, 0u);
           if (live && 2 * ck < g.n_seg) s0 = s_lut[window_bits(mybits, d, i1s, wrap(r2 + g.a2 + 2 * ck, d), g.L)];
           if (live && 2 * ck + 1 < g.n_seg) s1 = s_lut[window_bits(mybits, d, i1s, wrap(r2 + g.a2 + 2 * ck + 1, d), g.L)];
@@ -166,9 +173,12 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int kk = 0; kk < g.n_chunks; kk += 2)
+#pragma unroll
+      for (int kk = 0; kk < (NCH ? NCH : 16); kk += 2) {
+        if (kk >= n_chunks) break;
         mma_i8(tmem, umma_desc(a_addr + kk * A_LBO, A_LBO, 128), umma_desc(b_addr + kk * g.b_lbo, g.b_lbo, 128), idesc,
                kk > 0 ? 1u : 0u);
+      }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     {
@@ -215,9 +225,13 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
     // objective sums: a tile touches chains c0 and c0 + 1; exact integer atomics, normalised by the caller
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
-      const bool mine = live && (c - c0) == sl;
-      long long shi = warp_sum_ll(mine ? my_hi : 0), slo = warp_sum_ll(mine ? my_lo : 0);
-      int sn = warp_sum_i(mine ? my_n : 0);
+      const bool mine = live && sl_mine == sl;
+      const long long vh = mine ? my_hi : 0;        // |hi| < 2^42: three 21-bit limbs; lo < 2^20, n <= 1: one REDUX each
+      const long long shi = ((long long)__reduce_add_sync(SO_FULL, (int)(vh >> 42)) << 42) +
+                            ((long long)__reduce_add_sync(SO_FULL, (int)((vh >> 21) & 0x1fffff)) << 21) +
+                            (long long)__reduce_add_sync(SO_FULL, (int)(vh & 0x1fffff));
+      const long long slo = (long long)__reduce_add_sync(SO_FULL, (int)(mine ? my_lo : 0));
+      const int sn = __reduce_add_sync(SO_FULL, mine ? my_n : 0);
       if (lane == 0 && (shi | slo | sn) != 0 && c0 + sl < n_chains) {
         atomicAdd((unsigned long long *)(hi_out + c0 + sl), (unsigned long long)shi);
         atomicAdd((unsigned long long *)(lo_out + c0 + sl), (unsigned long long)slo);
@@ -238,6 +252,8 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
       }
       buf ^= 1;
     }
+    r0 += TILE_M;
+    if (r0 >= N) { r0 -= N; ++c0; }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -295,7 +311,7 @@ int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint3
   switch (s->HP4) {
 #define SO_TC_CASE(V)                                                                                              \
   case V: {                                                                                                        \
-    auto kern = score_tc_kernel<V>;                                                                                \
+    auto kern = (g.kw == 8 && g.n_chunks == 4) ? score_tc_kernel<V, 4> : score_tc_kernel<V, 0>;                    \
     SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
     kern<<<blocks, 128, smem, st>>>(bits_dev, lat->d, lat->N, lat->W, n, sv, g, (const uint4 *)s->tc_image_dev,    \
                                     hq_dev, hi, lo, nact);                                                         \
