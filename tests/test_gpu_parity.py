@@ -532,3 +532,92 @@ def test_batch_scoring_large(eng):
     assert (rate2 == rate).all() and (lh2 == lh).all() and (ne2 == ne).all()
     ref = S.eval_rate_fp64(p, L.generate_all_translations(x[7], d))
     assert abs(rate[7] - ref) <= 1e-5 * max(abs(ref), 1e-12)
+
+
+# ---- edge cases of the C ABI: empty / ragged ranges, invalid inputs, large lattices -----------------------------------
+def test_abi_edge_cases(eng):
+    import ctypes as C
+    from so_b200 import _lib as B
+    lat = eng.Lattice(12, "NH3")
+    ch = eng.Chains(lat, 8)
+    lib = ch.lib
+    # empty ranges are no-ops
+    assert lib.so_set_occupancy(ch.h, 3, 0, None) == 0 and lib.so_get_occupancy(ch.h, 8, 0, None) == 0
+    assert lib.so_descriptors(ch.h, 0, 0, None, None, None, None, None, None) == 0
+    assert lib.so_flip(ch.h, 0, None, None) == 0
+    # all outputs NULL: still valid
+    assert lib.so_descriptors(ch.h, 0, 8, None, None, None, None, None, None) == 0
+    # ranges past the end / negative
+    occ = np.zeros((8, 144), dtype=np.uint8)
+    for c0, n in ((1, 8), (-1, 2), (9, 0)):
+        assert lib.so_get_occupancy(ch.h, c0, n, occ.ctypes.data_as(B.c_u8p)) == B.SO_EINVAL
+    # calls that need a surrogate before one is attached
+    of = np.zeros(8)
+    assert lib.so_score(ch.h, 0, 8, of.ctypes.data_as(B.c_f64p)) == B.SO_EINVAL
+    a = B.AnnealArgs()
+    temps = np.ones(4)
+    a.n_steps, a.temps = 4, temps.ctypes.data_as(B.c_f64p)
+    assert lib.so_anneal(ch.h, C.byref(a), None) == B.SO_EINVAL and b"surrogate" in lib.so_last_error()
+    # bad surrogate shapes / aliasing offsets / tree out of range
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=1)
+    with pytest.raises(ValueError):
+        eng.SurrogateTables(eng.Lattice(6, "LSC"), p.offsets, p.W1, p.b1, p.w2, p.b2)     # 7x7 window aliases on 6x6
+    with pytest.raises(ValueError):
+        eng.SurrogateTables(lat, p.offsets, np.zeros((49, 40)), np.zeros(40), np.zeros(40), 0.0)   # H > 32
+    bad_tree = dict(feature=np.array([60, -2, -2]), thr=np.array([0.5, 0, 0]), left=np.array([1, -1, -1]),
+                    right=np.array([2, -1, -1]), active=np.array([0, 1, 0]))
+    with pytest.raises(ValueError):
+        eng.SurrogateTables(lat, p.offsets, p.W1, p.b1, p.w2, p.b2, tree=bad_tree)        # feature 60 >= K
+    tab = Hp.tables_from_params(lat, p)
+    ch.attach(tab)
+    # proposals out of range / proposals without uniforms
+    prop = np.full((8, 4), 144, dtype=np.int32)
+    with pytest.raises(ValueError):
+        ch.anneal(temps, proposals=prop, uniforms=np.zeros((8, 4), dtype=np.float32))
+    a.proposals = prop.ctypes.data_as(B.c_i32p)
+    assert lib.so_anneal(ch.h, C.byref(a), None) == B.SO_EINVAL
+    # zero steps: nothing happens, stats are zero
+    st = ch.anneal(np.zeros(0))
+    assert st["flips"] == 0 and st["accepted"] == 0
+    # ragged update keeps untouched chains' state
+    x = Hp.random_structures(8, 144, seed=2)
+    ch.set_occupancy(x)
+    of0 = ch.objective()
+    ch.set_occupancy(1 - x[2:5], chain0=2)
+    of1 = ch.objective()
+    assert (of1[[0, 1, 5, 6, 7]] == of0[[0, 1, 5, 6, 7]]).all() and (ch.score() == of1).all()
+    # exchange argument validation
+    import torch
+    buf = torch.zeros(8, dtype=torch.float64, device="cuda")
+    ns = C.c_int64()
+    for rank, world, ladder, parity in ((0, 1, 3, 0), (1, 1, 4, 0), (0, 1, 4, 2), (0, 1, 1, 0)):
+        rc = lib.so_exchange(ch.h, rank, world, ladder, parity, 1, 0, 0.05, C.c_void_p(buf.data_ptr()),
+                             C.c_void_p(buf.data_ptr()), None, C.byref(ns))
+        assert rc == B.SO_EINVAL
+
+
+def test_large_lattice_descriptors_and_flat_fallback(eng):
+    """d = 160 (25,600 sites): typing against the oracle, and SA through the generic kernel (the bit-plane of such a
+    lattice does not fit the pipelined kernel's shared-memory budget at 8 warps per CTA)."""
+    d = 160
+    N = d * d
+    x = Hp.random_structures(3, N, seed=8)
+    lat = eng.Lattice(d, "NH3")
+    ch = eng.Chains(lat, 3)
+    ch.set_occupancy(x)
+    out = ch.descriptors(c6=True, lsc_type=True, nh3_type=True, nh3_exp=True)
+    assert (out["c6"] == ST.c6_counts(x, d)).all() and (out["lsc_type"] == ST.lsc_types(x, d)).all()
+    nh3 = ST.nh3_types(x, d)
+    assert (out["nh3_type"] == nh3).all() and (out["nh3_exp"] == ST.nh3_export_hist(nh3)).all()
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=2)
+    ch.attach(Hp.tables_from_params(lat, p))
+    steps = 300
+    rng = np.random.default_rng(1)
+    prop = rng.integers(0, N, (3, steps)).astype(np.int32)
+    u = rng.random((3, steps), dtype=np.float32)
+    temps = SA.schedule("exp", 0.5, steps)
+    stats, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True)
+    from oracle import c_oracle
+    o = c_oracle.anneal_fixed_many(p, S.quantize(p), d, x, temps, prop, u)
+    assert (acc.astype(bool) == o["accept"]).all() and (ch.get_occupancy() == o["x"]).all()
+    assert (ch.objective() == o["OF"]).all()
