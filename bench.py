@@ -259,14 +259,17 @@ def run_gpu(a):
     # end-to-end through the public API with HOST buffers: H2D occupancy -> state build -> sweep -> D2H result
     e2e = None
     if a.e2e_steps > 0:
-        bits_host = ch.get_bits()
+        # pinned host buffers for the step's inputs and results
+        bits_host = torch.empty((n_local, lat.W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        of = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
+        ch.get_bits(out=bits_host)
         barrier()
         t0 = time.perf_counter()
         for s in range(a.e2e_steps):
             ch.set_bits(bits_host)                                   # H2D + first-layer state rebuild
             ch.anneal(temps_all[-N:], step0=(total_sweeps + s) * N, seed=a.seed, chain_id0=chain_id0)
-            bits_host = ch.get_bits()                                # D2H final occupancies
-            of = ch.objective()                                      # D2H objective per chain
+            ch.get_bits(out=bits_host)                               # D2H final occupancies
+            ch.objective(out=of)                                     # D2H objective per chain
         barrier()
         e2e_s = time.perf_counter() - t0
         if dist is not None:

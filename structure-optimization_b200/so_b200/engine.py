@@ -173,9 +173,12 @@ class Chains(object):
             bits = bits[None, :]
         B.check(self.lib.so_set_occupancy_bits(self.h, chain0, bits.shape[0], _p(bits, B.c_u32p)))
 
-    def get_bits(self, chain0=0, n=None):
+    def get_bits(self, chain0=0, n=None, out=None):
+        """Bit-planes of chains [chain0, chain0+n); `out` may be a preallocated (e.g. pinned) uint32 array."""
         n = self.n - chain0 if n is None else n
-        bits = np.empty((n, self.lattice.W), dtype=np.uint32)
+        bits = np.empty((n, self.lattice.W), dtype=np.uint32) if out is None else out
+        if bits.shape != (n, self.lattice.W) or bits.dtype != np.uint32 or not bits.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint32 array of shape (%d, %d)" % (n, self.lattice.W))
         B.check(self.lib.so_get_occupancy_bits(self.h, chain0, n, _p(bits, B.c_u32p)))
         return bits
 
@@ -223,9 +226,9 @@ class Chains(object):
         B.check(self.lib.so_score(self.h, chain0, n, _p(of, B.c_f64p)))
         return of
 
-    def objective(self, chain0=0, n=None, sums=False):
+    def objective(self, chain0=0, n=None, sums=False, out=None):
         n = self.n - chain0 if n is None else n
-        of = np.empty(n, dtype=np.float64)
+        of = np.empty(n, dtype=np.float64) if out is None else out
         if not sums:
             B.check(self.lib.so_objective(self.h, chain0, n, _p(of, B.c_f64p), None, None, None))
             return of
