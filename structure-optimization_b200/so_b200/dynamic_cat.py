@@ -211,6 +211,10 @@ class dynamic_cat(object):
     def get_local_inds(self, shift1=0, shift2=0):
         return [self.sym_inds_to_var_ind(d1 + shift1, d2 + shift2) for d2 in range(-3, 4) for d1 in range(-3, 4)]
 
+    def show(self, fname='structure_1', fmat='png'):
+        """OML/dynamic_cat.py:366-401 renders the slab with ASE (png / xsd / povray): visualisation is out of scope."""
+        raise NotImplementedError('show() needs ASE rendering, which is outside the B200 hot path')
+
     # ---- out-of-scope leftovers kept for API completeness (GA / distance metric, OML/dynamic_cat.py:188-220,404-437)
     def geo_crossover(self, x1, x2, pt1=1, pt2=1):
         x_bounds = [random.random() for i in range(pt1)]
