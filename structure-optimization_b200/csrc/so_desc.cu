@@ -8,6 +8,7 @@
 // against a literal NetworkX evaluation in tests/test_oracle_types.py).  Each chain's bit-plane is staged in
 // shared memory; histograms are reduced with warp ballots + popc.
 #include "so_internal.cuh"
+#include <stdlib.h>
 
 // ring order: consecutive entries are mutually adjacent
 __device__ __constant__ int8_t c_ring1[6] = {1, 0, -1, -1, 0, 1};
@@ -243,6 +244,188 @@ __global__ void __launch_bounds__(256) descriptors_kernel(const uint32_t *__rest
   }
 }
 
+// ---- bit-sliced histograms: 32 sites per integer operation ------------------------------------------------------
+// Every typing rule is a boolean function of neighbouring occupancy bits, so whole lattice rows are processed as
+// bit-vectors: a thread owns one 32-bit word of one row; neighbour access is a 1-bit rotation of a row (periodic in
+// i1) or the row above / below (periodic in i2); counts of Ni among 6 ring or 3 triangle sites are bit-sliced adders;
+// histograms are popc of the resulting type masks.  Three passes (layer 3 -> layers 4 and 2 -> vacancy refinements
+// and layer 1) exchange intermediate planes through shared memory.  Used when only histograms are requested.
+struct Planes {
+  uint32_t *X, *p3, *p5, *p45, *p12, *p14, *p8, *p15, *pn2;
+  int d, RW, tail;
+  uint32_t tailmask;
+};
+__device__ __forceinline__ uint32_t pl_get(const Planes &P, const uint32_t *pl, int row, int w) { return pl[row * P.RW + w]; }
+__device__ __forceinline__ uint32_t pl_valid(const Planes &P, int w) { return w == P.RW - 1 ? P.tailmask : 0xffffffffu; }
+// result bit i = pl[row][i + 1 mod d]
+__device__ __forceinline__ uint32_t pl_rotr1(const Planes &P, const uint32_t *pl, int row, int w) {
+  const uint32_t *r = pl + row * P.RW;
+  uint32_t x = r[w];
+  if (w < P.RW - 1) return (x >> 1) | (r[w + 1] << 31);
+  return ((x >> 1) | ((r[0] & 1u) << (P.tail - 1))) & P.tailmask;
+}
+// result bit i = pl[row][i - 1 mod d]
+__device__ __forceinline__ uint32_t pl_rotl1(const Planes &P, const uint32_t *pl, int row, int w) {
+  const uint32_t *r = pl + row * P.RW;
+  uint32_t in = w > 0 ? (r[w - 1] >> 31) : ((r[P.RW - 1] >> (P.tail - 1)) & 1u);
+  return ((r[w] << 1) | in) & pl_valid(P, w);
+}
+// NON-periodic: result bit i = pl[row][i + o] if 0 <= i + o < d else 0; rows outside [0, d) read as 0
+__device__ __forceinline__ uint32_t pl_shift_np(const Planes &P, const uint32_t *pl, int row, int w, int o) {
+  if (row < 0 || row >= P.d) return 0u;
+  const uint32_t *r = pl + row * P.RW;
+  uint32_t x = r[w], out;
+  if (o == 0) out = x;
+  else if (o > 0) out = (x >> o) | (w + 1 < P.RW ? r[w + 1] << (32 - o) : 0u);
+  else out = (x << -o) | (w > 0 ? r[w - 1] >> (32 + o) : 0u);
+  return out & pl_valid(P, w);
+}
+__device__ __forceinline__ void add3(uint32_t a, uint32_t b, uint32_t c, uint32_t &s0, uint32_t &s1) {
+  s0 = a ^ b ^ c;
+  s1 = (a & b) | (c & (a ^ b));
+}
+
+__global__ void __launch_bounds__(128) descriptors_bits_kernel(const uint32_t *__restrict__ bits, int d, int N, int W,
+                                                               int32_t *lsc_hist, int32_t *nh3_hist, int32_t *nh3_exp,
+                                                               int want_nh3) {
+  extern __shared__ uint32_t s_pl[];
+  __shared__ int s_hist[24];
+  const long long chain = blockIdx.x;
+  Planes P;
+  P.d = d; P.RW = (d + 31) / 32; P.tail = d - 32 * (P.RW - 1);
+  P.tailmask = P.tail == 32 ? 0xffffffffu : ((1u << P.tail) - 1u);
+  const int items = d * P.RW;
+  P.X = s_pl; P.p3 = P.X + items; P.p5 = P.p3 + items; P.p45 = P.p5 + items; P.p12 = P.p45 + items;
+  P.p14 = P.p12 + items; P.p8 = P.p14 + items; P.p15 = P.p8 + items; P.pn2 = P.p15 + items;
+  if (threadIdx.x < 24) s_hist[threadIdx.x] = 0;
+  // row-aligned copy of the packed bit-plane (site v = row*d + i1)
+  const uint32_t *src = bits + chain * W;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    int row = it / P.RW, w = it - row * P.RW;
+    int v0 = row * d + 32 * w, wi = v0 >> 5;
+    uint32_t lo = src[wi], hi = wi + 1 < W ? src[wi + 1] : 0u;
+    P.X[it] = __funnelshift_r(lo, hi, v0 & 31) & pl_valid(P, w);
+  }
+  __syncthreads();
+  int cnt[20];
+#pragma unroll
+  for (int t = 0; t < 20; ++t) cnt[t] = 0;
+  int lsc1 = 0, lsc2 = 0;
+  // ---- pass A: layer 3, Ni sites: c6 by a bit-sliced adder, types 3 / 5 / 4 (LSC 1 / 2) ---------------------------
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    int row = it / P.RW, w = it - row * P.RW;
+    int rp = row + 1 == d ? 0 : row + 1, rm = row == 0 ? d - 1 : row - 1;
+    uint32_t x = P.X[it];
+    uint32_t r0 = pl_rotr1(P, P.X, row, w), r1 = pl_get(P, P.X, rp, w), r2 = pl_rotl1(P, P.X, rp, w);
+    uint32_t r3 = pl_rotl1(P, P.X, row, w), r4 = pl_get(P, P.X, rm, w), r5 = pl_rotr1(P, P.X, rm, w);
+    uint32_t s1, c1, s2, c2, b1, b2;
+    add3(r0, r1, r2, s1, c1);
+    add3(r3, r4, r5, s2, c2);
+    uint32_t b0 = s1 ^ s2, k = s1 & s2;
+    add3(c1, c2, k, b1, b2);
+    uint32_t eq6 = b2 & b1 & ~b0, eq4 = b2 & ~b1 & ~b0;
+    uint32_t adj = ~(r0 | r1) | ~(r1 | r2) | ~(r2 | r3) | ~(r3 | r4) | ~(r4 | r5) | ~(r5 | r0);
+    uint32_t t3 = x & eq6, t5 = x & eq4 & adj, t4 = x & ~t3 & ~t5;
+    P.p3[it] = t3; P.p5[it] = t5; P.p45[it] = t4 | t5;
+    lsc1 += __popc(t3); lsc2 += __popc(t5);
+    cnt[3] += __popc(t3); cnt[5] += __popc(t5); cnt[4] += __popc(t4);
+  }
+  if (want_nh3) {
+    __syncthreads();
+    // ---- pass B: layer 4 (triangle under it: (0,-1),(1,-1),(0,0)) and layer 2 (over it: (1,-1),(0,0),(1,0)) -------
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      int row = it / P.RW, w = it - row * P.RW;
+      int rm = row == 0 ? d - 1 : row - 1;
+      uint32_t valid = pl_valid(P, w);
+      {
+        uint32_t a = pl_get(P, P.X, rm, w), b = pl_rotr1(P, P.X, rm, w), c = pl_get(P, P.X, row, w), n0, n1, e0, e1;
+        add3(a, b, c, n0, n1);
+        add3(pl_get(P, P.p45, rm, w), pl_rotr1(P, P.p45, rm, w), pl_get(P, P.p45, row, w), e0, e1);
+        uint32_t all3 = n0 & n1;
+        uint32_t t1 = all3 & ~e0 & ~e1, t17 = all3 & e0 & ~e1, t16 = all3 & e1, t12 = n0 & ~n1, t14 = ~n0 & n1;
+        P.p12[it] = t12; P.p14[it] = t14;
+        cnt[1] += __popc(t1); cnt[17] += __popc(t17); cnt[16] += __popc(t16); cnt[12] += __popc(t12); cnt[14] += __popc(t14);
+      }
+      {
+        uint32_t a = pl_rotr1(P, P.X, rm, w), b = pl_get(P, P.X, row, w), c = pl_rotr1(P, P.X, row, w), n0, n1, t0, t1m, e0, e1m;
+        add3(a, b, c, n0, n1);
+        add3(pl_rotr1(P, P.p3, rm, w), pl_get(P, P.p3, row, w), pl_rotr1(P, P.p3, row, w), t0, t1m);
+        add3(pl_rotr1(P, P.p5, rm, w), pl_get(P, P.p5, row, w), pl_rotr1(P, P.p5, row, w), e0, e1m);
+        uint32_t all3 = n0 & n1;
+        uint32_t t18 = all3 & (~t0 & t1m) & (e0 & ~e1m), t19 = all3 & (t0 & ~t1m) & (~e0 & e1m);
+        uint32_t t2 = all3 & ~t18 & ~t19, t8 = ~n0 & ~n1 & valid, t15 = ~n0 & n1, tn = n0 & ~n1;
+        P.p8[it] = t8; P.p15[it] = t15; P.pn2[it] = tn;
+        cnt[18] += __popc(t18); cnt[19] += __popc(t19); cnt[2] += __popc(t2); cnt[8] += __popc(t8); cnt[15] += __popc(t15);
+      }
+    }
+    __syncthreads();
+    // ---- pass C: layer-3 vacancies (11 / 10 / 9 / 6) and layer 1 (7 / 13) ------------------------------------------
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      int row = it / P.RW, w = it - row * P.RW;
+      int rp = row + 1 == d ? 0 : row + 1, rm = row == 0 ? d - 1 : row - 1;
+      uint32_t valid = pl_valid(P, w);
+      {
+        uint32_t vac = ~P.X[it] & valid;
+        // layer-4 atoms above a site: (0,0), (-1,1), (0,1)
+        uint32_t has14 = pl_get(P, P.p14, row, w) | pl_rotl1(P, P.p14, rp, w) | pl_get(P, P.p14, rp, w);
+        uint32_t has12 = pl_get(P, P.p12, row, w) | pl_rotl1(P, P.p12, rp, w) | pl_get(P, P.p12, rp, w);
+        uint32_t t11 = vac & has14, t10 = vac & has12 & ~has14, rest = vac & ~has12 & ~has14;
+        // type-15 layer-2 atoms within 2*2.77 A on RAW (non-periodic) positions: 12 index offsets (k - i)
+        uint32_t near = 0;
+        if (rest) {
+          near |= pl_shift_np(P, P.p15, row, w, -2) | pl_shift_np(P, P.p15, row + 1, w, -2) | pl_shift_np(P, P.p15, row + 2, w, -2);
+          near |= pl_shift_np(P, P.p15, row - 1, w, -1) | pl_shift_np(P, P.p15, row, w, -1) |
+                  pl_shift_np(P, P.p15, row + 1, w, -1) | pl_shift_np(P, P.p15, row + 2, w, -1);
+          near |= pl_shift_np(P, P.p15, row - 1, w, 0) | pl_shift_np(P, P.p15, row, w, 0) | pl_shift_np(P, P.p15, row + 1, w, 0);
+          near |= pl_shift_np(P, P.p15, row - 1, w, 1) | pl_shift_np(P, P.p15, row, w, 1);
+        }
+        uint32_t t9 = rest & near, t6 = rest & ~near;
+        cnt[11] += __popc(t11); cnt[10] += __popc(t10); cnt[9] += __popc(t9); cnt[6] += __popc(t6);
+      }
+      {
+        // layer-2 atoms above a layer-1 atom: (-1,0), (0,-1), (0,0)
+        uint32_t a = pl_rotl1(P, P.p8, row, w), b = pl_get(P, P.p8, rm, w), c = pl_get(P, P.p8, row, w), n0, n1, z0, z1;
+        add3(a, b, c, n0, n1);
+        add3(pl_rotl1(P, P.pn2, row, w), pl_get(P, P.pn2, rm, w), pl_get(P, P.pn2, row, w), z0, z1);
+        uint32_t t7 = n0 & n1 & valid, t13 = (~n0 & n1) & (z0 & ~z1) & valid;
+        cnt[7] += __popc(t7); cnt[13] += __popc(t13);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 1; t < 20; ++t) {
+    int v = __reduce_add_sync(SO_FULL, cnt[t]);
+    if (lane == 0 && v) atomicAdd(&s_hist[t], v);
+  }
+  lsc1 = __reduce_add_sync(SO_FULL, lsc1);
+  lsc2 = __reduce_add_sync(SO_FULL, lsc2);
+  if (lane == 0) { if (lsc1) atomicAdd(&s_hist[21], lsc1); if (lsc2) atomicAdd(&s_hist[22], lsc2); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (lsc_hist) {
+      lsc_hist[chain * 3 + 0] = N - s_hist[21] - s_hist[22];
+      lsc_hist[chain * 3 + 1] = s_hist[21];
+      lsc_hist[chain * 3 + 2] = s_hist[22];
+    }
+    if (want_nh3) {
+      int typed = 0;
+      for (int t = 1; t < 20; ++t) typed += s_hist[t];
+      if (nh3_hist) {
+        nh3_hist[chain * 20] = 5 * N - typed;
+        for (int t = 1; t < 20; ++t) nh3_hist[chain * 20 + t] = s_hist[t];
+      }
+      if (nh3_exp) {
+        int e1 = s_hist[1], e2 = s_hist[3], e3 = s_hist[5], e4 = s_hist[16], e5 = s_hist[17], e6 = s_hist[18],
+            e7 = s_hist[19];
+        int32_t *o = nh3_exp + chain * 8;
+        o[0] = 5 * N - (e1 + e2 + e3 + e4 + e5 + e6 + e7);
+        o[1] = e1; o[2] = e2; o[3] = e3; o[4] = e4; o[5] = e5; o[6] = e6; o[7] = e7;
+      }
+    }
+  }
+}
+
 // ---- per-flip descriptor deltas: one warp per chain, one affected node per lane -----------------------
 struct AffTable {
   int n;
@@ -340,6 +523,18 @@ int so_launch_descriptors(const so_lattice *lat, const uint32_t *bits_dev, int64
                           uint8_t *nh3_type, int32_t *lsc_hist, int32_t *nh3_hist, int32_t *nh3_exp, cudaStream_t st) {
   if (n == 0) return SO_OK;
   int want_nh3 = (nh3_type || nh3_hist || nh3_exp) ? 1 : 0;
+  {
+    // histograms only: the bit-sliced kernel (32 sites per integer operation); SO_DESC_BITS=0 keeps the per-site kernel
+    const char *env = getenv("SO_DESC_BITS");
+    size_t smem = (size_t)9 * lat->d * ((lat->d + 31) / 32) * 4;
+    if (!c6 && !lsc_type && !nh3_type && smem <= 96 * 1024 && !(env && env[0] == '0')) {
+      SO_CUDA(cudaFuncSetAttribute(descriptors_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      descriptors_bits_kernel<<<(unsigned)n, 128, smem, st>>>(bits_dev, lat->d, lat->N, lat->W, lsc_hist, nh3_hist, nh3_exp,
+                                                              want_nh3);
+      SO_CUDA(cudaGetLastError());
+      return SO_OK;
+    }
+  }
   int threads = lat->N >= 256 ? 256 : ((lat->N + 31) / 32) * 32;
   descriptors_kernel<<<(unsigned)n, threads, lat->W * sizeof(uint32_t), st>>>(
       bits_dev, lat->d, lat->N, lat->W, lat->h5_ptr_dev, lat->h5_idx_dev, c6, lsc_type, nh3_type, lsc_hist, nh3_hist,

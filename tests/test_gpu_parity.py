@@ -621,3 +621,32 @@ def test_large_lattice_descriptors_and_flat_fallback(eng):
     o = c_oracle.anneal_fixed_many(p, S.quantize(p), d, x, temps, prop, u)
     assert (acc.astype(bool) == o["accept"]).all() and (ch.get_occupancy() == o["x"]).all()
     assert (ch.objective() == o["OF"]).all()
+
+
+@pytest.mark.parametrize("d", [4, 5, 7, 12, 16, 31, 32, 33, 40, 64, 96])
+def test_descriptor_histograms_bit_sliced(eng, d):
+    """Histogram-only requests run the bit-sliced kernel (32 sites per integer op, popc): bit-exact vs the oracle for
+    lattice edges below, at and above the 32-bit word size, incl. the non-periodic type-9 rule near the cell edge."""
+    N = d * d
+    n = 24 if d >= 64 else 80
+    x = np.vstack([Hp.random_structures(n, N, seed=300 + d), np.zeros((1, N), np.uint8), np.ones((1, N), np.uint8),
+                   Hp.random_structures(8, N, seed=301 + d, coverage=0.08), Hp.random_structures(8, N, seed=302 + d, coverage=0.93)])
+    lat = eng.Lattice(d, "NH3")
+    ch = eng.Chains(lat, len(x))
+    ch.set_occupancy(x)
+    out = ch.descriptors(lsc_hist=True, nh3_hist=True, nh3_exp=True)
+    lsc = ST.lsc_types(x, d)
+    nh3 = ST.nh3_types(x, d)
+    assert (out["lsc_hist"] == np.stack([(lsc == t).sum(1) for t in range(3)], 1)).all()
+    want = ST.nh3_hist(nh3)
+    assert (out["nh3_hist"] == want).all(), np.argwhere(out["nh3_hist"] != want)[:5]
+    assert (out["nh3_exp"] == ST.nh3_export_hist(nh3)).all()
+    os.environ["SO_DESC_BITS"] = "0"                              # the per-site kernel gives the same histograms
+    try:
+        ref = ch.descriptors(lsc_hist=True, nh3_hist=True, nh3_exp=True)
+    finally:
+        del os.environ["SO_DESC_BITS"]
+    assert all((ref[k] == out[k]).all() for k in out)
+    lsc_only = eng.Chains(eng.Lattice(d, "LSC"), len(x))
+    lsc_only.set_occupancy(x)
+    assert (lsc_only.descriptors(lsc_hist=True)["lsc_hist"] == out["lsc_hist"]).all()
