@@ -662,12 +662,8 @@ int so_score_batch(so_lattice *L, so_surrogate *s, int64_t n, const uint32_t *bi
       SO_CUDA(cudaMemcpyAsync(rate + c0, b_of.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
     }
     if (lsc_hist || nh3_exp) {
-      for (int64_t g0 = 0; g0 < nc; g0 += 65535) {   // one block per structure
-        int64_t ng = std::min<int64_t>(65535, nc - g0);
-        SO_TRY(so_launch_descriptors(L, b_bits.as<uint32_t>() + g0 * L->W, ng, nullptr, nullptr, nullptr,
-                                     lsc_hist ? b_lh.as<int32_t>() + g0 * 3 : nullptr, nullptr,
-                                     nh3_exp ? b_ne.as<int32_t>() + g0 * 8 : nullptr, st));
-      }
+      SO_TRY(so_launch_descriptors(L, b_bits.as<uint32_t>(), nc, nullptr, nullptr, nullptr, lsc_hist ? b_lh.as<int32_t>() : nullptr,
+                                   nullptr, nh3_exp ? b_ne.as<int32_t>() : nullptr, st));
       if (lsc_hist) SO_CUDA(cudaMemcpyAsync(lsc_hist + c0 * 3, b_lh.p, (size_t)nc * 12, cudaMemcpyDeviceToHost, st));
       if (nh3_exp) SO_CUDA(cudaMemcpyAsync(nh3_exp + c0 * 8, b_ne.p, (size_t)nc * 32, cudaMemcpyDeviceToHost, st));
     }
