@@ -101,12 +101,17 @@ class SurrogateTables(object):
         B.check(self.lib.so_eval_rows(self.h, n, _p(Xb, B.c_u8p), _p(active, B.c_u8p), _p(rate, B.c_f64p)))
         return active.astype(bool), rate
 
-    def score_batch(self, bits, want_lsc_hist=False, want_nh3_exp=False):
+    def score_batch(self, bits, want_lsc_hist=False, want_nh3_exp=False, out=None):
+        """rate[n] (+ LSC / NH3-exported histograms) of n bit-packed structures; `out` = (rate, lsc_hist, nh3_exp)
+        preallocated (e.g. pinned) arrays."""
         bits = np.ascontiguousarray(bits, dtype=np.uint32)
         n = bits.shape[0]
-        rate = np.empty(n, dtype=np.float64)
-        lh = np.empty((n, 3), dtype=np.int32) if want_lsc_hist else None
-        ne = np.empty((n, 8), dtype=np.int32) if want_nh3_exp else None
+        if out is not None:
+            rate, lh, ne = out
+        else:
+            rate = np.empty(n, dtype=np.float64)
+            lh = np.empty((n, 3), dtype=np.int32) if want_lsc_hist else None
+            ne = np.empty((n, 8), dtype=np.int32) if want_nh3_exp else None
         B.check(self.lib.so_score_batch(self.lattice.h, self.h, n, _p(bits, B.c_u32p), _p(rate, B.c_f64p),
                                         _p(lh, B.c_i32p), _p(ne, B.c_i32p)))
         return rate, lh, ne
