@@ -290,3 +290,30 @@ def test_analytical_sa_matches_oracle():
                    n_record=4, return_stats=True)
     o = SA.optimize_analytical(xs[0], d, SA.schedule("exp", 0.05, 288), prop[0][:288], u[0][:288])
     assert cat.variable_occs == [int(v) for v in o["x"]] and abs(out["OF"] - o["OF"]) <= 1e-9 * abs(o["OF"])
+
+
+def test_optimize_on_nh3_cat_default_lattice():
+    """NH3_cat() default: 16x16, full 256-column translation descriptor (generic SA kernel, 16x16-window tensor-core
+    state build); decisions and final structure against the C oracle, then the exported KMC site types."""
+    from so_b200 import NH3_cat, optimize
+    from oracle import c_oracle
+    d, N = 16, 256
+    p = S.SurrogateParams.random_init(L.full_offsets(d), H=20, seed=12, y_mean=0.1, y_scale=0.7)
+    cat = NH3_cat()
+    random.seed(2)
+    cat.randomize(coverage=0.6)
+    x0 = np.array(cat.variable_occs, dtype=np.uint8)
+    n_cycles = 4
+    steps = n_cycles * N
+    rng = np.random.default_rng(3)
+    prop = rng.integers(0, N, steps).astype(np.int32)
+    u = rng.random(steps, dtype=np.float32)
+    out = optimize(cat, surrogate=duck_surrogate(p), n_cycles=n_cycles, T_0=0.2, proposals=prop, uniforms=u,
+                   exact_guard=False, return_stats=True)
+    o = c_oracle.anneal_fixed_many(p, S.quantize(p), d, x0[None, :], SA.schedule("exp", 0.2, steps), prop[None, :], u[None, :])
+    assert cat.variable_occs == [int(v) for v in o["x"][0]] and out["OF"] == o["OF"][0]
+    assert out["accepted"] == int(o["accept"].sum())
+    ref = S.eval_rate_fp64(p, L.generate_all_translations(o["x"][0], d))
+    assert abs(out["OF"] - ref) <= 1e-5 * abs(ref)
+    cat.graph_to_KMClattice()
+    assert cat.KMC_lat.site_type_inds == ST.nh3_export(o["x"][0], d)
