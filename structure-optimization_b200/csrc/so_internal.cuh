@@ -40,6 +40,7 @@ struct so_surrogate {
   int32_t *t_feature_dev, *t_left_dev, *t_right_dev;
   double *t_thr_dev;
   uint8_t *t_active_dev;
+  int4 *t_packed_dev;                   // one record per node: {offset of the tested column (o1 | o2<<16), left, right, flags}
   std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
   int win_ok, win_a1, win_b1, win_a2, win_b2;   // descriptor offsets form the full rectangle [a1,b1] x [a2,b2]
   int32_t *Wst_dev;                             // W1q rows in staged (memory) order of the window
@@ -77,6 +78,7 @@ struct SurView {
   const int32_t *t_feature, *t_left, *t_right;
   const double *t_thr;
   const uint8_t *t_active;
+  const int4 *t_packed;                 // flags: 1 leaf, 2 leaf is active, 4 go left when the bit is 0, 8 ... when it is 1
 };
 
 struct SaParams {
@@ -108,7 +110,7 @@ inline SurView make_view(const so_surrogate *s) {
   v.offs = s->offs_dev; v.W1q = s->W1q_dev; v.b1q = s->b1q_dev; v.w2q = s->w2q_dev;
   v.W1d = s->W1d_dev; v.b1d = s->b1d_dev; v.w2d = s->w2d_dev;
   v.t_feature = s->t_feature_dev; v.t_left = s->t_left_dev; v.t_right = s->t_right_dev;
-  v.t_thr = s->t_thr_dev; v.t_active = s->t_active_dev;
+  v.t_thr = s->t_thr_dev; v.t_active = s->t_active_dev; v.t_packed = s->t_packed_dev;
   return v;
 }
 
@@ -194,16 +196,15 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SO_F
 // ---- tree gate ----------------------------------------------------------------------------------------
 // Descriptor column c of row (r1,r2) is the site (r1+o1[c], r2+o2[c]).
 __device__ __forceinline__ int tree_gate(const SurView &sv, const BitView &b, int r1, int r2) {
-  int node = 0;
-  int f = __ldg(sv.t_feature);
-  while (f >= 0) {
-    int off = __ldg(sv.offs + f);
-    int o1 = (int)(short)(off & 0xffff), o2 = off >> 16;
+  // one 16-byte record per node visit (the test "x <= thr" on a 0/1 input is two precomputed flag bits)
+  int4 nd = __ldg(sv.t_packed);
+  while (!(nd.w & 1)) {
+    int o1 = (int)(short)(nd.x & 0xffff), o2 = nd.x >> 16;
     int bit = b.at(r1 + o1, r2 + o2);
-    node = ((double)bit <= __ldg(sv.t_thr + node)) ? __ldg(sv.t_left + node) : __ldg(sv.t_right + node);
-    f = __ldg(sv.t_feature + node);
+    int go_left = (nd.w >> (2 + bit)) & 1;
+    nd = __ldg(sv.t_packed + (go_left ? nd.y : nd.z));
   }
-  return (int)__ldg(sv.t_active + node);
+  return (nd.w >> 1) & 1;
 }
 
 
