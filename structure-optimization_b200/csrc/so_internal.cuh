@@ -195,6 +195,39 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SO_F
 
 // ---- tree gate ----------------------------------------------------------------------------------------
 // Descriptor column c of row (r1,r2) is the site (r1+o1[c], r2+o2[c]).
+// gate of row (r1,r2) before and after flipping site f in ONE walk: both walks share the path until a node tests the
+// flipped site (if none does, the gate cannot change)
+__device__ __forceinline__ void tree_gate_pair(const SurView &sv, const uint32_t *bits, int d, int r1, int r2, int f,
+                                               int &g0, int &g1) {
+  int4 nd = __ldg(sv.t_packed);
+  while (!(nd.w & 1)) {
+    int o1 = (int)(short)(nd.x & 0xffff), o2 = nd.x >> 16;
+    int v = wrap(r2 + o2, d) * d + wrap(r1 + o1, d);
+    int bit = (bits[v >> 5] >> (v & 31)) & 1;
+    if (v == f) {                                   // the two structures part ways here
+      int4 na = __ldg(sv.t_packed + (((nd.w >> (2 + bit)) & 1) ? nd.y : nd.z));
+      int4 nb = __ldg(sv.t_packed + (((nd.w >> (3 - bit)) & 1) ? nd.y : nd.z));
+      while (!(na.w & 1)) {
+        int a1 = (int)(short)(na.x & 0xffff), a2 = na.x >> 16;
+        int va = wrap(r2 + a2, d) * d + wrap(r1 + a1, d);
+        int ba = (bits[va >> 5] >> (va & 31)) & 1;
+        na = __ldg(sv.t_packed + (((na.w >> (2 + ba)) & 1) ? na.y : na.z));
+      }
+      while (!(nb.w & 1)) {
+        int a1 = (int)(short)(nb.x & 0xffff), a2 = nb.x >> 16;
+        int vb = wrap(r2 + a2, d) * d + wrap(r1 + a1, d);
+        int bb = ((bits[vb >> 5] >> (vb & 31)) & 1) ^ (vb == f);
+        nb = __ldg(sv.t_packed + (((nb.w >> (2 + bb)) & 1) ? nb.y : nb.z));
+      }
+      g0 = (na.w >> 1) & 1;
+      g1 = (nb.w >> 1) & 1;
+      return;
+    }
+    nd = __ldg(sv.t_packed + (((nd.w >> (2 + bit)) & 1) ? nd.y : nd.z));
+  }
+  g0 = g1 = (nd.w >> 1) & 1;
+}
+
 __device__ __forceinline__ int tree_gate(const SurView &sv, const BitView &b, int r1, int r2) {
   // one 16-byte record per node visit (the test "x <= thr" on a 0/1 input is two precomputed flag bits)
   int4 nd = __ldg(sv.t_packed);

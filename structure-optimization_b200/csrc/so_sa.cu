@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(128) sa_gated_kernel(SaParams P) {
           A1 += (long long)w2[p].x * max(h.x + sgn * w.x, 0) + (long long)w2[p].y * max(h.y + sgn * w.y, 0) +
                 (long long)w2[p].z * max(h.z + sgn * w.z, 0) + (long long)w2[p].w * max(h.w + sgn * w.w, 0);
         }
-        int g0 = sv.gated ? tree_gate(sv, b0, r1, r2) : 1;
-        int g1 = sv.gated ? tree_gate(sv, b1, r1, r2) : 1;
+        int g0 = 1, g1 = 1;
+        if (sv.gated) tree_gate_pair(sv, s_bits, d, r1, r2, f, g0, g1);
         if (g1) { dhi += A1 >> SO_SPLIT_BITS; dlo += A1 & SO_SPLIT_MASK; }
         if (g0) { dhi -= A0 >> SO_SPLIT_BITS; dlo -= A0 & SO_SPLIT_MASK; }
         dn += g1 - g0;
