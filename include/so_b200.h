@@ -134,7 +134,8 @@ typedef struct so_anneal_args {
   uint8_t *accept_out;       /* optional accept/reject log                         */
   int exact_guard;           /* 1: re-decide near-ties with fp64 weights           */
   double guard_tol;          /* |delta - T ln u| below which the guard fires       */
-  int variant;               /* 0 = auto; 1 = force the row-per-lane kernel (tests) */
+  int variant;               /* 0 = auto; tests: 1 = row-per-lane global-memory kernel, 2 = generic flat kernel,
+                                3 = auto without the shared-memory-resident kernel of small lattices */
 } so_anneal_args;
 
 typedef struct so_anneal_stats {

@@ -589,7 +589,9 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
   int dev = c->lat->device, n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
-  if (!s->gated && P.variant == 0 && s->win_ok && s->K * s->HP4 <= 256 &&
+  // small lattices: the whole chain state stays in shared memory for the launch (so_sa_resident.cu)
+  if (P.variant == 0 && so_resident_plan(s, P.N, P.W, nullptr, nullptr)) return so_launch_anneal_resident(c, P, st);
+  if (!s->gated && (P.variant == 0 || P.variant == 3) && s->win_ok && s->K * s->HP4 <= 256 &&
       so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 113 * 1024) {
     return so_launch_anneal_window(c, P, st);
   }

@@ -1,0 +1,418 @@
+// so_sa_resident.cu -- SA for SMALL lattices (the reference's own regime, d = 12 / 16): the whole first-layer state of a
+// chain (4*N*Hp bytes, 11.5 KB at N = 144, H = 20) lives in shared memory for the entire launch, so a step touches no
+// HBM at all.  Same arithmetic and decisions as the other SA kernels (exact integer sums, fp64 Metropolis rule), any
+// descriptor (full translation row or window), with or without the tree gate.
+//
+//   * one warp per chain; the CTA shares the weight table W1q, the descriptor offsets and the tree;
+//   * delta of the rows that are active before AND after the flip: lanes own a fixed hidden-unit quad and stride over
+//     the affected rows (32/HP4 rows per pass), accumulating relu differences per component in int32 (a column's
+//     differences are bounded by sum_k |W1q_kj| < 2^30); the second-layer weights enter once per step, the warp sum is
+//     three REDUX on 21-bit limbs;
+//   * tree gate: two caches per chain make a step almost walk-free.  (1) the gate of every row of the CURRENT
+//     structure, one bit per row.  (2) the path index S[v] (K bits per site v): bit c is set iff the current path of
+//     row v - offset_c tests column c, i.e. site v.  A flip at f can only change the gates of the rows in S[f] (about
+//     depth/K of them), so only those walk the tree; on accept their old path entries are dropped and the new ones
+//     entered.  Rows whose gate changes contribute their whole row sum (rare, out of line);
+//   * draws come lane-parallel 32 steps at a time (Philox or the injected sequence); the decision uses the fp32
+//     pre-filter of the window kernel and the fp64 rule when that cannot decide.
+#include "so_internal.cuh"
+#include <math.h>
+
+namespace {
+
+struct DrawR {
+  int f;        // packed (f1 | f2 << 16)
+  float u;
+  float tf;
+};
+// lane-parallel draws of steps 32b .. 32b+31; everything by value (an address-taken argument would pin the caller's
+// variables in local memory)
+__device__ __noinline__ DrawR draw_batch_res(const double *temps, const int32_t *proposals, const float *uniforms,
+                                             long long n_steps, long long step0, long long chain_id, long long c,
+                                             unsigned long long seed, int N, int d, long long b, int lane) {
+  long long s = b * 32 + lane;
+  DrawR r;
+  int f = 0;
+  r.u = 0.f;
+  r.tf = 0.f;
+  if (s < n_steps) {
+    r.tf = (float)__ldg(temps + s);
+    if (proposals) {
+      f = __ldg(proposals + c * n_steps + s);
+      r.u = __ldg(uniforms + c * n_steps + s);
+    } else {
+      unsigned long long step = (unsigned long long)(step0 + s), cid = (unsigned long long)chain_id;
+      uint32_t o[4];
+      philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)seed,
+                    (uint32_t)(seed >> 32), o);
+      f = (int)__umulhi(o[0], (uint32_t)N);
+      r.u = (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+    }
+  }
+  int f2 = f / d;
+  r.f = (f - f2 * d) | (f2 << 16);
+  return r;
+}
+
+// the fp64 Metropolis rule (OML/optimize_SA.py:108-116) + near-tie guard test; bit 0 accept, bit 1 guard
+__device__ __noinline__ int decide_res(double delta, double tsc, const double *temps, long long s, float u, int exact_guard,
+                                       double tol) {
+  const double T = __dmul_rn(tsc, __ldg(temps + s));
+  bool accept, guard = false;
+  if (delta > 0.0) {
+    accept = true;
+    if (exact_guard && T <= 0.0 && delta < tol) guard = true;
+  } else if (T > 0.0) {
+    accept = exp(delta / T) > (double)u;
+    if (exact_guard && u > 0.f) guard = fabs(delta - T * log((double)u)) < tol;
+  } else {
+    accept = false;
+    if (exact_guard && delta > -tol) guard = true;
+  }
+  return (accept ? 1 : 0) | (guard ? 2 : 0);
+}
+__device__ __noinline__ int exact_decision_res(const SurView sv, const uint32_t *bits, int d, int f, int lane, double tsc,
+                                               const double *temps, long long s, float u) {
+  const double T = __dmul_rn(tsc, __ldg(temps + s));
+  double de = so_exact_delta(sv, bits, d, f, lane);
+  if (de > 0.0) return 1;
+  if (T > 0.0) return exp(de / T) > (double)u ? 1 : 0;
+  return 0;
+}
+
+// whole row sum  sum_j w2q_j * relu(hq_rj + sgn * W1q_kj)  (sgn = 0: the row as it is); rows whose gate changes only
+__device__ __noinline__ long long row_sum_res(const int4 *hrow, const int4 *wrow, const int32_t *w2q, int hp4, int sgn) {
+  long long A = 0;
+  for (int p = 0; p < hp4; ++p) {
+    const int4 h = hrow[p], w = wrow[p], w2 = __ldg((const int4 *)w2q + p);
+    A += (long long)w2.x * max(h.x + sgn * w.x, 0) + (long long)w2.y * max(h.y + sgn * w.y, 0) +
+         (long long)w2.z * max(h.z + sgn * w.z, 0) + (long long)w2.w * max(h.w + sgn * w.w, 0);
+  }
+  return A;
+}
+
+__host__ __device__ __forceinline__ size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Walk row (r1, r2) through the tree for the structure `bits` with site f read inverted (f = -1: as it is).
+__device__ __forceinline__ int walk1(const int4 *tree, const uint32_t *bits, int d, int f, int r1, int r2) {
+  int4 nd = tree[0];
+  while (!(nd.w & 1)) {
+    const int o1 = (int)(short)(nd.x & 0xffff), o2 = nd.x >> 16;
+    const int v = wrap(r2 + o2, d) * d + wrap(r1 + o1, d);
+    const int bit = (int)((bits[v >> 5] >> (v & 31)) & 1) ^ (v == f);
+    nd = tree[((nd.w >> (2 + bit)) & 1) ? nd.y : nd.z];
+  }
+  return (nd.w >> 1) & 1;
+}
+// The same walk on the structure as it is, entering (SET) or dropping the path in the index S: every node whose test
+// depends on its bit marks (site tested, column tested).  Returns the gate.
+template <bool SET>
+__device__ __noinline__ int walk_mark(const int4 *tree, const uint32_t *bits, uint32_t *S, int KW, int d, int r1, int r2) {
+  int4 nd = tree[0];
+  while (!(nd.w & 1)) {
+    const int o1 = (int)(short)(nd.x & 0xffff), o2 = nd.x >> 16;
+    const int v = wrap(r2 + o2, d) * d + wrap(r1 + o1, d);
+    const int bit = (int)((bits[v >> 5] >> (v & 31)) & 1);
+    if (((nd.w >> 2) ^ (nd.w >> 3)) & 1) {
+      const int c = nd.w >> 8;
+      if (SET) atomicOr(S + v * KW + (c >> 5), 1u << (c & 31));
+      else atomicAnd(S + v * KW + (c >> 5), ~(1u << (c & 31)));
+    }
+    nd = tree[((nd.w >> (2 + bit)) & 1) ? nd.y : nd.z];
+  }
+  return (nd.w >> 1) & 1;
+}
+
+template <int HP4, bool GATED>
+__global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int RPP = 32 / HP4;          // rows per pass
+  constexpr int STRIDE = RPP * HP4;      // working lanes
+  const SurView &sv = P.sv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d, N = P.N, K = sv.K, KW = (K + 31) >> 5, W = P.W;
+  const int n_tree = GATED ? sv.n_tree : 0;
+  // shared layout: [W1q: K*HP4 int4][tree: n_tree int4][offsets: K] | per warp: [hq: N*HP4 int4][bits W][act W]
+  // [path index S: N*KW][row flags: K bytes]
+  int4 *s_W = (int4 *)s_raw;
+  int4 *s_tree = s_W + (size_t)K * HP4;
+  int32_t *s_off = (int32_t *)(s_tree + n_tree);
+  unsigned char *s_chain0 = (unsigned char *)s_off + a16((size_t)K * 4);
+  const size_t per_warp = (size_t)N * HP4 * 16 + a16((size_t)(2 * W + (GATED ? N * KW : 0)) * 4 + (size_t)K);
+  int4 *s_hq = (int4 *)(s_chain0 + (size_t)warp * per_warp);
+  uint32_t *s_bits = (uint32_t *)(s_hq + (size_t)N * HP4);
+  uint32_t *s_act = s_bits + W;
+  uint32_t *s_S = s_act + W;
+  unsigned char *s_flag = (unsigned char *)(s_S + (GATED ? N * KW : 0));
+  for (int q = threadIdx.x; q < K * HP4; q += blockDim.x) s_W[q] = ((const int4 *)sv.W1q)[q];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
+  if (GATED) {
+    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree[i] = sv.t_packed[i];
+  }
+  __syncthreads();
+  const int part = lane % HP4, rsub = lane / HP4;
+  const bool worker = lane < STRIDE;
+  const int4 w2 = worker ? __ldg((const int4 *)sv.w2q + part) : make_int4(0, 0, 0, 0);
+  const float tol_f = (float)P.guard_tol;
+  const bool guard_on = P.exact_guard != 0;
+
+  for (;;) {
+    long long c = 0;
+    if (lane == 0) c = (long long)atomicAdd(P.counters, 1ULL);
+    c = __shfl_sync(SO_FULL, c, 0);
+    if (c >= P.n_chains) break;
+    uint32_t *bits_g = P.bits + c * W;
+    int4 *hq_g = (int4 *)P.hq + c * (long long)N * HP4;
+    for (int w = lane; w < W; w += 32) s_bits[w] = bits_g[w];
+    for (int q = lane; q < N * HP4; q += 32) s_hq[q] = hq_g[q];
+    long long hi = P.hi[c], lo = P.lo[c];
+    int nact = P.nact[c];
+    const double tsc = P.tscale[c];
+    const float tsc_f = (float)tsc;
+    unsigned n_acc = 0, n_guard = 0;
+    __syncwarp();
+    if (GATED) {      // gates and path index of the starting structure: row r = 32 j + lane -> bit `lane` of word j
+      for (int i = lane; i < N * KW; i += 32) s_S[i] = 0u;
+      __syncwarp();
+      for (int r0 = 0; r0 < N; r0 += 32) {
+        const int r = r0 + lane;
+        int g = 0;
+        if (r < N) {
+          const int r2 = r / d;
+          g = walk_mark<true>(s_tree, s_bits, s_S, KW, d, r - r2 * d, r2);
+        }
+        __syncwarp();
+        const unsigned m = __ballot_sync(SO_FULL, g);
+        if (lane == 0) s_act[r0 >> 5] = m;
+      }
+      __syncwarp();
+    }
+    DrawR batch;
+    batch.f = 0; batch.u = 0.f; batch.tf = 0.f;
+
+    for (long long s = 0; s < P.n_steps; ++s) {
+      if ((s & 31) == 0)
+        batch = draw_batch_res(P.temps, P.proposals, P.uniforms, P.n_steps, P.step0, P.chain_id0 + c, c, P.seed, N, d,
+                               s >> 5, lane);
+      const int fp = __shfl_sync(SO_FULL, batch.f, (int)(s & 31));
+      const float u = __shfl_sync(SO_FULL, batch.u, (int)(s & 31));
+      const float Tf = tsc_f * __shfl_sync(SO_FULL, batch.tf, (int)(s & 31));
+      const int f1 = fp & 0xffff, f2 = fp >> 16;
+      const int f = f2 * d + f1;
+      const int sgn = ((s_bits[f >> 5] >> (f & 31)) & 1) ? -1 : 1;
+      long long dhi = 0;
+      int dlo = 0, dn = 0;
+
+      // per-lane bit masks over the lane's rows (row of group j: k = 32 j + lane): path tests f / gate changes
+      unsigned mywalk = 0, mychg = 0;
+      if (GATED) {
+        unsigned g0m = 0;
+#pragma unroll 2
+        for (int j = 0; j < KW; ++j) {
+          const int k = 32 * j + lane;
+          const bool valid = k < K;
+          const int off = s_off[valid ? k : 0];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const unsigned g0 = valid ? (s_act[row >> 5] >> (row & 31)) & 1u : 0u;
+          g0m |= g0 << j;
+          mywalk |= ((s_S[f * KW + j] >> lane) & 1u) << j;
+        }
+        // only rows whose current path tests site f can change their gate: walk those for the flipped structure
+        unsigned g1m = g0m;
+        for (unsigned todo = mywalk; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1;
+          const int off = s_off[32 * j + lane];
+          const unsigned g1 = walk1(s_tree, s_bits, d, f, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+          g1m = (g1m & ~(1u << j)) | (g1 << j);
+        }
+        __syncwarp();
+        const unsigned both = g0m & g1m;
+        mychg = g0m ^ g1m;
+        for (int j = 0; j < KW; ++j)
+          if (32 * j + lane < K) s_flag[32 * j + lane] = (unsigned char)((both >> j) & 1u);
+        // rows that switch on or off contribute their whole row sum (rare)
+        for (unsigned todo = mychg; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1, k = 32 * j + lane;
+          const int off = s_off[k];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const int on = (g1m >> j) & 1;
+          const long long A = row_sum_res(s_hq + row * HP4, s_W + k * HP4, sv.w2q, HP4, on ? sgn : 0);
+          const int sg = on ? 1 : -1;
+          dhi += sg * (A >> SO_SPLIT_BITS);
+          dlo += sg * (int)(A & SO_SPLIT_MASK);
+          dn += sg;
+        }
+        __syncwarp();
+      }
+
+      // relu differences of the rows active on both sides (all rows without a gate)
+      int ax = 0, ay = 0, az = 0, aw = 0;
+      if (worker) {
+#pragma unroll 4
+        for (int k = rsub; k < K; k += RPP) {
+          const int m = GATED ? -(int)s_flag[k] : -1;        // branch-free: the passes stay independent
+          const int off = s_off[k];
+          const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
+          const int4 h = s_hq[(r2 * d + r1) * HP4 + part], w = s_W[k * HP4 + part];
+          ax += (max(h.x + sgn * w.x, 0) - max(h.x, 0)) & m;
+          ay += (max(h.y + sgn * w.y, 0) - max(h.y, 0)) & m;
+          az += (max(h.z + sgn * w.z, 0) - max(h.z, 0)) & m;
+          aw += (max(h.w + sgn * w.w, 0) - max(h.w, 0)) & m;
+        }
+      }
+      long long acc = (long long)w2.x * ax + (long long)w2.y * ay + (long long)w2.z * az + (long long)w2.w * aw;
+      {  // exact warp sum: |acc| < 2^62 -> three 21-bit limbs, one REDUX each
+        int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
+        l0 = __reduce_add_sync(SO_FULL, l0);
+        l1 = __reduce_add_sync(SO_FULL, l1);
+        l2 = __reduce_add_sync(SO_FULL, l2);
+        acc = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
+      }
+      long long dlo_w = acc & SO_SPLIT_MASK;
+      if (GATED && __any_sync(SO_FULL, mychg != 0)) {
+        int l0 = (int)(dhi & 0x1fffff), l1 = (int)((dhi >> 21) & 0x1fffff), l2 = (int)(dhi >> 42);
+        l0 = __reduce_add_sync(SO_FULL, l0);
+        l1 = __reduce_add_sync(SO_FULL, l1);
+        l2 = __reduce_add_sync(SO_FULL, l2);
+        dhi = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
+        dn = __reduce_add_sync(SO_FULL, dn);
+        // |dlo| per lane < 2^20 * rows per lane: the warp sum fits int32 for K <= 1024
+        dlo_w += (long long)__reduce_add_sync(SO_FULL, dlo);
+      }
+      dhi += acc >> SO_SPLIT_BITS;
+      const double delta = so_real(sv.c, sv.b2, sv.y_scale, sv.y_mean, dhi, dlo_w, dn);
+      bool accept;
+      {
+        // fp32 pre-filter: decides when p = exp(delta/T) is at least 1e-3 (relative) away from u; with the exact guard
+        // on, only where that margin also rules out |delta - T ln u| < tol  (tol / T < 2.5e-4)
+        const float pf = __expf(__fdividef((float)delta, Tf));
+        if (delta > 0.0 && (Tf > 0.f || !guard_on)) {
+          accept = true;
+        } else if (delta <= 0.0 && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u) &&
+                   (!guard_on || tol_f < 2.5e-4f * Tf)) {
+          accept = pf > u;
+        } else {
+          int r = decide_res(delta, tsc, P.temps, s, u, P.exact_guard, P.guard_tol);
+          if (r & 2) {
+            r = exact_decision_res(sv, s_bits, d, f, lane, tsc, P.temps, s, u);
+            ++n_guard;
+          }
+          accept = r & 1;
+        }
+      }
+      if (accept) {
+        if (GATED && __any_sync(SO_FULL, mywalk != 0)) {     // paths through f are about to change: drop them from the index
+          for (int j = 0; j < KW; ++j)
+            if ((mywalk >> j) & 1) {
+              const int off = s_off[32 * j + lane];
+              walk_mark<false>(s_tree, s_bits, s_S, KW, d, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+            }
+          __syncwarp();
+        }
+        if (worker) {
+#pragma unroll 4
+          for (int k = rsub; k < K; k += RPP) {
+            const int off = s_off[k];
+            const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
+            int4 *hp = s_hq + (r2 * d + r1) * HP4 + part;
+            int4 h = *hp;
+            const int4 w = s_W[k * HP4 + part];
+            h.x += sgn * w.x; h.y += sgn * w.y; h.z += sgn * w.z; h.w += sgn * w.w;
+            *hp = h;
+          }
+        }
+        if (GATED) {
+          for (unsigned todo = mychg; todo; todo &= todo - 1) {
+            const int off = s_off[32 * (__ffs(todo) - 1) + lane];
+            const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+            atomicXor(s_act + (row >> 5), 1u << (row & 31));
+          }
+        }
+        if (lane == 0) s_bits[f >> 5] ^= (1u << (f & 31));
+        if (GATED && __any_sync(SO_FULL, mywalk != 0)) {     // ... and enter the paths of the new structure
+          __syncwarp();
+          for (int j = 0; j < KW; ++j)
+            if ((mywalk >> j) & 1) {
+              const int off = s_off[32 * j + lane];
+              walk_mark<true>(s_tree, s_bits, s_S, KW, d, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+            }
+        }
+        lo += dlo_w;
+        hi += dhi + (lo >> SO_SPLIT_BITS);
+        lo &= SO_SPLIT_MASK;
+        nact += dn;
+        ++n_acc;
+      }
+      if (P.accept_out && lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
+      __syncwarp();
+    }
+    for (int w = lane; w < W; w += 32) bits_g[w] = s_bits[w];
+    for (int q = lane; q < N * HP4; q += 32) hq_g[q] = s_hq[q];
+    if (lane == 0) {
+      P.hi[c] = hi;
+      P.lo[c] = lo;
+      P.nact[c] = nact;
+      if (n_acc) atomicAdd(P.counters + 1, (unsigned long long)n_acc);
+      if (n_guard) atomicAdd(P.counters + 2, (unsigned long long)n_guard);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+// Warps per CTA and its shared memory, maximising the resident chains of an SM; false if the state does not fit
+// (or the tree is too large to share).
+bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out) {
+  const size_t kSmemSM = 228 * 1024, kSmemCTA = 227 * 1024;
+  const int KW = (s->K + 31) / 32;
+  const int n_tree = s->gated ? s->n_tree : 0;
+  if (n_tree > 2048 || s->K > 1024 || s->HP4 > 8) return false;
+  const size_t shared = (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4);
+  const size_t per_warp = (size_t)N * s->HP4 * 16 + a16((size_t)(2 * W + (s->gated ? N * KW : 0)) * 4 + (size_t)s->K);
+  int best_w = 0, best_total = 0;
+  size_t best_smem = 0;
+  const int cand[] = {4, 5, 6, 8, 10, 12, 16};
+  for (int w : cand) {
+    size_t smem = shared + (size_t)w * per_warp;
+    if (smem > kSmemCTA) continue;
+    int per_sm = (int)(kSmemSM / (smem + 1024));
+    if (per_sm * w > 64) per_sm = 64 / w;
+    if (per_sm * w > best_total) { best_total = per_sm * w; best_w = w; best_smem = smem; }
+  }
+  if (best_total < 8) return false;       // too few resident chains to keep an SM busy: the global-memory kernels win
+  if (warps_out) *warps_out = best_w;
+  if (smem_out) *smem_out = best_smem;
+  return true;
+}
+
+int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st) {
+  const so_surrogate *s = c->sur;
+  int n_sm = 0, warps = 0;
+  size_t smem = 0;
+  SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+  if (!so_resident_plan(s, P.N, P.W, &warps, &smem)) { so_set_error("resident kernel: state does not fit"); return SO_EINVAL; }
+  const int per_sm = (int)((228 * 1024) / (smem + 1024));
+  long long want = (P.n_chains + warps - 1) / warps;
+  int blocks = (int)(want < (long long)n_sm * per_sm ? want : (long long)n_sm * per_sm);
+  if (blocks < 1) blocks = 1;
+#define SO_RES_CASE(V)                                                                                       \
+  case V: {                                                                                                  \
+    if (s->gated) {                                                                                          \
+      auto kern = sa_resident_kernel<V, true>;                                                               \
+      SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+      kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
+    } else {                                                                                                 \
+      auto kern = sa_resident_kernel<V, false>;                                                              \
+      SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+      kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
+    }                                                                                                        \
+  } break;
+  switch (s->HP4) {
+    SO_RES_CASE(1) SO_RES_CASE(2) SO_RES_CASE(3) SO_RES_CASE(4) SO_RES_CASE(5) SO_RES_CASE(6) SO_RES_CASE(7) SO_RES_CASE(8)
+    default: so_set_error("hidden width not supported"); return SO_EINVAL;
+  }
+#undef SO_RES_CASE
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}

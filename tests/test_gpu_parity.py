@@ -234,8 +234,9 @@ def _run_sa(eng, d, p, n_chains, steps, seed, T0=0.05, variant=0, use_philox=Fal
     return dict(x0=x0, x1=x1, acc=acc, prop=prop, u=u, temps=temps, of=of, stats=stats)
 
 
-def test_sa_flat_full_descriptor(eng):
-    _run_sa(eng, 12, Hp.golden_surrogate(gated=False), n_chains=24, steps=1500, seed=21)
+@pytest.mark.parametrize("variant", [0, 2])
+def test_sa_flat_full_descriptor(eng, variant):
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=False), n_chains=24, steps=1500, seed=21, variant=variant)
 
 
 def test_sa_flat_local_descriptor(eng):
@@ -243,46 +244,53 @@ def test_sa_flat_local_descriptor(eng):
     _run_sa(eng, 16, p, n_chains=40, steps=2000, seed=22)
 
 
+# variant 0 picks the shared-memory-resident kernel on these small lattices, variant 3 the pipelined window kernel
+@pytest.mark.parametrize("variant", [0, 3])
 @pytest.mark.parametrize("T0", [0.05, 2.0])
-def test_sa_flat_local_small_lattice_wrap(eng, T0):
+def test_sa_flat_local_small_lattice_wrap(eng, T0, variant):
     """7x7 window on a 7x7 lattice: every wrap path, and (hot run: most flips accepted) every prefetched window is
     stale -- the hazard paths of the pipelined kernel."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=4)
-    r = _run_sa(eng, 7, p, n_chains=16, steps=800, seed=23, T0=T0, cooling="const" if T0 > 1 else "exp")
+    r = _run_sa(eng, 7, p, n_chains=16, steps=800, seed=23, T0=T0, cooling="const" if T0 > 1 else "exp", variant=variant)
     if T0 > 1:
         assert r["acc"].mean() > 0.5
 
 
+@pytest.mark.parametrize("variant", [0, 3])
 @pytest.mark.parametrize("d", [8, 12, 20])
-def test_sa_window_hot_chains(eng, d):
+def test_sa_window_hot_chains(eng, d, variant):
     """High acceptance on small lattices: overlapping windows of consecutive flips are the common case."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=40 + d)
-    r = _run_sa(eng, d, p, n_chains=32, steps=1500, seed=50 + d, T0=1.0, cooling="const")
+    r = _run_sa(eng, d, p, n_chains=32, steps=1500, seed=50 + d, T0=1.0, cooling="const", variant=variant)
     assert r["acc"].mean() > 0.1
 
 
-def test_sa_window_many_chains(eng):
+@pytest.mark.parametrize("variant", [0, 3])
+def test_sa_window_many_chains(eng, variant):
     """More chains than resident warps: dynamic chain hand-out + stage/mbarrier reuse across chains."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=41)
-    _run_sa(eng, 12, p, n_chains=5000, steps=70, seed=51, T0=0.5, check_chains=range(0, 5000, 97), cooling="const")
+    _run_sa(eng, 12, p, n_chains=5000, steps=70, seed=51, T0=0.5, check_chains=range(0, 5000, 97), cooling="const",
+            variant=variant)
 
 
-def test_sa_gated_full_descriptor(eng):
-    _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_sa_gated_full_descriptor(eng, variant):
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24, variant=variant)
 
 
 def test_sa_kernel_variants_agree(eng):
-    """window (pipelined) == generic flat == row-per-lane kernels, bit for bit."""
+    """resident == window (pipelined) == generic flat == row-per-lane kernels, bit for bit."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
     a = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=0, T0=0.3)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         b = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=variant, T0=0.3)
         assert (a["acc"] == b["acc"]).all() and (a["x1"] == b["x1"]).all() and (a["of"] == b["of"]).all()
 
 
-def test_sa_philox_draws(eng):
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_sa_philox_draws(eng, variant):
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=6)
-    _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=26, use_philox=True)
+    _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=26, use_philox=True, variant=variant)
 
 
 def test_sa_odd_hidden_width(eng):
