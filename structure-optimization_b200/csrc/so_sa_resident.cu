@@ -81,14 +81,16 @@ __device__ __noinline__ int exact_decision_res(const SurView sv, const uint32_t 
 }
 
 // whole row sum  sum_j w2q_j * relu(hq_rj + sgn * W1q_kj)  (sgn = 0: the row as it is); rows whose gate changes only
-__device__ __noinline__ long long row_sum_res(const int4 *hrow, const int4 *wrow, const int32_t *w2q, int hp4, int sgn) {
-  long long A = 0;
-  for (int p = 0; p < hp4; ++p) {
-    const int4 h = hrow[p], w = wrow[p], w2 = __ldg((const int4 *)w2q + p);
-    A += (long long)w2.x * max(h.x + sgn * w.x, 0) + (long long)w2.y * max(h.y + sgn * w.y, 0) +
-         (long long)w2.z * max(h.z + sgn * w.z, 0) + (long long)w2.w * max(h.w + sgn * w.w, 0);
+template <int HP4>
+__device__ __forceinline__ long long row_sum_res(const int4 *hrow, const int4 *wrow, const int4 *w2s, int sgn) {
+  long long A = 0, B = 0;
+#pragma unroll
+  for (int p = 0; p < HP4; ++p) {
+    const int4 h = hrow[p], w = wrow[p], w2 = w2s[p];
+    A += (long long)w2.x * max(h.x + sgn * w.x, 0) + (long long)w2.y * max(h.y + sgn * w.y, 0);
+    B += (long long)w2.z * max(h.z + sgn * w.z, 0) + (long long)w2.w * max(h.w + sgn * w.w, 0);
   }
-  return A;
+  return A + B;
 }
 
 __host__ __device__ __forceinline__ size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -132,20 +134,23 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d, N = P.N, K = sv.K, KW = (K + 31) >> 5, W = P.W;
   const int n_tree = GATED ? sv.n_tree : 0;
-  // shared layout: [W1q: K*HP4 int4][tree: n_tree int4][offsets: K] | per warp: [hq: N*HP4 int4][bits W][act W]
-  // [path index S: N*KW][row flags: K bytes]
+  // shared layout: [W1q: K*HP4 int4][tree: n_tree int4][offsets: K][w2q: HP4 int4] | per warp: [hq: N*HP4 int4][bits W][act W]
+  // [path index S: N*KW][active rows of the step: K u32][their positions: K u16]
   int4 *s_W = (int4 *)s_raw;
   int4 *s_tree = s_W + (size_t)K * HP4;
   int32_t *s_off = (int32_t *)(s_tree + n_tree);
-  unsigned char *s_chain0 = (unsigned char *)s_off + a16((size_t)K * 4);
-  const size_t per_warp = (size_t)N * HP4 * 16 + a16((size_t)(2 * W + (GATED ? N * KW : 0)) * 4 + (size_t)K);
+  int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
+  unsigned char *s_chain0 = (unsigned char *)(s_w2 + HP4);
+  const size_t per_warp = (size_t)N * HP4 * 16 + a16((size_t)(2 * W + (GATED ? N * KW + K : 0)) * 4 + (GATED ? (size_t)K * 2 : 0));
   int4 *s_hq = (int4 *)(s_chain0 + (size_t)warp * per_warp);
   uint32_t *s_bits = (uint32_t *)(s_hq + (size_t)N * HP4);
   uint32_t *s_act = s_bits + W;
   uint32_t *s_S = s_act + W;
-  unsigned char *s_flag = (unsigned char *)(s_S + (GATED ? N * KW : 0));
+  uint32_t *s_list = s_S + (GATED ? N * KW : 0);            // compacted active rows of the step (gated)
+  unsigned short *s_pos = (unsigned short *)(s_list + (GATED ? K : 0));
   for (int q = threadIdx.x; q < K * HP4; q += blockDim.x) s_W[q] = ((const int4 *)sv.W1q)[q];
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
+  if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)sv.w2q)[threadIdx.x];
   if (GATED) {
     for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree[i] = sv.t_packed[i];
   }
@@ -205,8 +210,10 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
 
       // per-lane bit masks over the lane's rows (row of group j: k = 32 j + lane): path tests f / gate changes
       unsigned mywalk = 0, mychg = 0;
+      int n_list = 0;            // rows active before the flip, compacted: s_list[i] = k << 16 | live << 15 | row
       if (GATED) {
         unsigned g0m = 0;
+        const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 2
         for (int j = 0; j < KW; ++j) {
           const int k = 32 * j + lane;
@@ -216,6 +223,13 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
           const unsigned g0 = valid ? (s_act[row >> 5] >> (row & 31)) & 1u : 0u;
           g0m |= g0 << j;
           mywalk |= ((s_S[f * KW + j] >> lane) & 1u) << j;
+          const unsigned m = __ballot_sync(SO_FULL, g0);
+          if (g0) {
+            const int pos = n_list + __popc(m & lt);
+            s_list[pos] = (unsigned)(k << 16) | 0x8000u | (unsigned)row;
+            s_pos[k] = (unsigned short)pos;
+          }
+          n_list += __popc(m);
         }
         // only rows whose current path tests site f can change their gate: walk those for the flipped structure
         unsigned g1m = g0m;
@@ -226,17 +240,15 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
           g1m = (g1m & ~(1u << j)) | (g1 << j);
         }
         __syncwarp();
-        const unsigned both = g0m & g1m;
         mychg = g0m ^ g1m;
-        for (int j = 0; j < KW; ++j)
-          if (32 * j + lane < K) s_flag[32 * j + lane] = (unsigned char)((both >> j) & 1u);
-        // rows that switch on or off contribute their whole row sum (rare)
+        // rows that switch on or off leave the difference pass and contribute their whole row sum
         for (unsigned todo = mychg; todo; todo &= todo - 1) {
           const int j = __ffs(todo) - 1, k = 32 * j + lane;
           const int off = s_off[k];
           const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
           const int on = (g1m >> j) & 1;
-          const long long A = row_sum_res(s_hq + row * HP4, s_W + k * HP4, sv.w2q, HP4, on ? sgn : 0);
+          if (!on) s_list[s_pos[k]] &= ~0x8000u;
+          const long long A = row_sum_res<HP4>(s_hq + row * HP4, s_W + k * HP4, s_w2, on ? sgn : 0);
           const int sg = on ? 1 : -1;
           dhi += sg * (A >> SO_SPLIT_BITS);
           dlo += sg * (int)(A & SO_SPLIT_MASK);
@@ -248,16 +260,28 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
       // relu differences of the rows active on both sides (all rows without a gate)
       int ax = 0, ay = 0, az = 0, aw = 0;
       if (worker) {
+        if (GATED) {
 #pragma unroll 4
-        for (int k = rsub; k < K; k += RPP) {
-          const int m = GATED ? -(int)s_flag[k] : -1;        // branch-free: the passes stay independent
-          const int off = s_off[k];
-          const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
-          const int4 h = s_hq[(r2 * d + r1) * HP4 + part], w = s_W[k * HP4 + part];
-          ax += (max(h.x + sgn * w.x, 0) - max(h.x, 0)) & m;
-          ay += (max(h.y + sgn * w.y, 0) - max(h.y, 0)) & m;
-          az += (max(h.z + sgn * w.z, 0) - max(h.z, 0)) & m;
-          aw += (max(h.w + sgn * w.w, 0) - max(h.w, 0)) & m;
+          for (int i = rsub; i < n_list; i += RPP) {
+            const unsigned e = s_list[i];
+            const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
+            const int4 h = s_hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
+            ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
+            ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
+            az += max(h.z + sg * w.z, 0) - max(h.z, 0);
+            aw += max(h.w + sg * w.w, 0) - max(h.w, 0);
+          }
+        } else {
+#pragma unroll 4
+          for (int k = rsub; k < K; k += RPP) {
+            const int off = s_off[k];
+            const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+            const int4 h = s_hq[row * HP4 + part], w = s_W[k * HP4 + part];
+            ax += max(h.x + sgn * w.x, 0) - max(h.x, 0);
+            ay += max(h.y + sgn * w.y, 0) - max(h.y, 0);
+            az += max(h.z + sgn * w.z, 0) - max(h.z, 0);
+            aw += max(h.w + sgn * w.w, 0) - max(h.w, 0);
+          }
         }
       }
       long long acc = (long long)w2.x * ax + (long long)w2.y * ay + (long long)w2.z * az + (long long)w2.w * aw;
@@ -313,8 +337,7 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
 #pragma unroll 4
           for (int k = rsub; k < K; k += RPP) {
             const int off = s_off[k];
-            const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
-            int4 *hp = s_hq + (r2 * d + r1) * HP4 + part;
+            int4 *hp = s_hq + (wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d)) * HP4 + part;
             int4 h = *hp;
             const int4 w = s_W[k * HP4 + part];
             h.x += sgn * w.x; h.y += sgn * w.y; h.z += sgn * w.z; h.w += sgn * w.w;
@@ -367,9 +390,9 @@ bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_
   const size_t kSmemSM = 228 * 1024, kSmemCTA = 227 * 1024;
   const int KW = (s->K + 31) / 32;
   const int n_tree = s->gated ? s->n_tree : 0;
-  if (n_tree > 2048 || s->K > 1024 || s->HP4 > 8) return false;
-  const size_t shared = (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4);
-  const size_t per_warp = (size_t)N * s->HP4 * 16 + a16((size_t)(2 * W + (s->gated ? N * KW : 0)) * 4 + (size_t)s->K);
+  if (n_tree > 2048 || s->K > 1024 || s->HP4 > 8 || N > 32767) return false;
+  const size_t shared = (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4) + (size_t)s->HP4 * 16;
+  const size_t per_warp = (size_t)N * s->HP4 * 16 + a16((size_t)(2 * W + (s->gated ? N * KW + s->K : 0)) * 4 + (s->gated ? (size_t)s->K * 2 : 0));
   int best_w = 0, best_total = 0;
   size_t best_smem = 0;
   const int cand[] = {4, 5, 6, 8, 10, 12, 16};
