@@ -231,7 +231,7 @@ int so_chains_destroy(so_chains *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->bits_dev); cudaFree(c->hq_dev); cudaFree(c->hi_dev); cudaFree(c->lo_dev); cudaFree(c->nact_dev);
-  cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch);
+  cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -743,6 +743,7 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   P.accept_out = a->accept_out ? d_acc.as<uint8_t>() : nullptr;
   P.exact_guard = a->exact_guard; P.guard_tol = a->guard_tol; P.variant = a->variant;
   P.counters = c->counters_dev;
+  P.gate_scratch = nullptr;
   P.sv = make_view(c->sur);
   SO_CUDA(cudaEventRecord(c->ev0, c->stream));
   SO_TRY(so_launch_anneal(c, P, c->stream));

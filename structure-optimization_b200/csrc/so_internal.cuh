@@ -64,6 +64,8 @@ struct so_chains {
   int64_t xch_cap;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
+  mutable uint32_t *gate_scratch;       // path index of the resident warps of the cached-gate kernel (so_sa_resident.cu)
+  mutable size_t gate_scratch_bytes;
   CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
   int tmap_ok;
 };
@@ -103,6 +105,7 @@ struct SaParams {
   double guard_tol;
   int variant;                          // 0 auto, 1 row-per-lane (gated) kernel, 2 generic flat kernel, 3 auto without the resident kernel
   unsigned long long *counters;
+  uint32_t *gate_scratch;
   SurView sv;
 };
 
@@ -142,6 +145,8 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);
 bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem);
+bool so_gate_index_ok(const so_surrogate *s, int N, int W);
+int so_launch_anneal_gate_index(const so_chains *c, const SaParams &P, cudaStream_t st);
 int so_launch_apply_flips(const so_chains *c, int64_t n, const int64_t *chains_dev, const int32_t *sites_dev,
                           cudaStream_t st);
 int so_lsc_max_sites(void);

@@ -93,6 +93,8 @@ __device__ __forceinline__ long long row_sum_res(const int4 *hrow, const int4 *w
   return A + B;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __host__ __device__ __forceinline__ size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // Walk row (r1, r2) through the tree for the structure `bits` with site f read inverted (f = -1: as it is).
@@ -125,8 +127,11 @@ __device__ __noinline__ int walk_mark(const int4 *tree, const uint32_t *bits, ui
   return (nd.w >> 1) & 1;
 }
 
-template <int HP4, bool GATED>
-__global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
+// RES: first-layer state (and the path index) of the chain in shared memory for the whole launch.  !RES (large
+// lattices, gated only): the same step with hq in global memory -- only the rows that are active are ever read --
+// and the path index in a per-warp global scratch; occupancy and gate bits stay in shared memory.
+template <int HP4, bool GATED, bool RES>
+__global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kernel(SaParams P) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr int RPP = 32 / HP4;          // rows per pass
   constexpr int STRIDE = RPP * HP4;      // working lanes
@@ -141,12 +146,15 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
   int32_t *s_off = (int32_t *)(s_tree + n_tree);
   int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
   unsigned char *s_chain0 = (unsigned char *)(s_w2 + HP4);
-  const size_t per_warp = (size_t)N * HP4 * 16 + a16((size_t)(2 * W + (GATED ? N * KW + K : 0)) * 4 + (GATED ? (size_t)K * 2 : 0));
+  const size_t per_warp = (RES ? (size_t)N * HP4 * 16 : 0) +
+                          a16((size_t)(2 * W + (GATED ? (RES ? N * KW : 0) + K : 0)) * 4 + (GATED ? (size_t)K * 2 : 0));
   int4 *s_hq = (int4 *)(s_chain0 + (size_t)warp * per_warp);
-  uint32_t *s_bits = (uint32_t *)(s_hq + (size_t)N * HP4);
+  uint32_t *s_bits = (uint32_t *)(s_hq + (RES ? (size_t)N * HP4 : 0));
   uint32_t *s_act = s_bits + W;
-  uint32_t *s_S = s_act + W;
-  uint32_t *s_list = s_S + (GATED ? N * KW : 0);            // compacted active rows of the step (gated)
+  uint32_t *s_S;
+  if constexpr (RES) s_S = s_act + W;
+  else s_S = P.gate_scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * N * KW;
+  uint32_t *s_list = s_act + W + (GATED && RES ? N * KW : 0);   // compacted active rows of the step (gated)
   unsigned short *s_pos = (unsigned short *)(s_list + (GATED ? K : 0));
   for (int q = threadIdx.x; q < K * HP4; q += blockDim.x) s_W[q] = ((const int4 *)sv.W1q)[q];
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
@@ -169,7 +177,13 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
     uint32_t *bits_g = P.bits + c * W;
     int4 *hq_g = (int4 *)P.hq + c * (long long)N * HP4;
     for (int w = lane; w < W; w += 32) s_bits[w] = bits_g[w];
-    for (int q = lane; q < N * HP4; q += 32) s_hq[q] = hq_g[q];
+    int4 *hq;
+    if constexpr (RES) {
+      for (int q = lane; q < N * HP4; q += 32) s_hq[q] = hq_g[q];
+      hq = s_hq;
+    } else {
+      hq = hq_g;
+    }
     long long hi = P.hi[c], lo = P.lo[c];
     int nact = P.nact[c];
     const double tsc = P.tscale[c];
@@ -205,6 +219,27 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
       const int f1 = fp & 0xffff, f2 = fp >> 16;
       const int f = f2 * d + f1;
       const int sgn = ((s_bits[f >> 5] >> (f & 31)) & 1) ? -1 : 1;
+      if constexpr (!RES) {
+        // global state: pull the next step's index words and active rows towards the SM while this step computes
+        // (a hint only; the draws of a batch are known 32 steps ahead)
+        if (((s + 1) & 31) != 0) {
+          const int fn = __shfl_sync(SO_FULL, batch.f, (int)((s + 1) & 31));
+          const int n1 = fn & 0xffff, n2 = fn >> 16;
+          if (lane < KW) prefetch_l1(s_S + (n2 * d + n1) * KW + lane);
+          for (int j = 0; j < KW; ++j) {
+            const int k = 32 * j + lane;
+            if (k < K) {
+              const int off = s_off[k];
+              const int row = wrap(n2 - (off >> 16), d) * d + wrap(n1 - (int)(short)(off & 0xffff), d);
+              if ((s_act[row >> 5] >> (row & 31)) & 1u) {
+                const char *p = (const char *)(hq + row * HP4);
+                prefetch_l1(p);
+                if ((((size_t)p) & 127) + HP4 * 16 > 128) prefetch_l1(p + HP4 * 16 - 1);
+              }
+            }
+          }
+        }
+      }
       long long dhi = 0;
       int dlo = 0, dn = 0;
 
@@ -248,7 +283,7 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
           const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
           const int on = (g1m >> j) & 1;
           if (!on) s_list[s_pos[k]] &= ~0x8000u;
-          const long long A = row_sum_res<HP4>(s_hq + row * HP4, s_W + k * HP4, s_w2, on ? sgn : 0);
+          const long long A = row_sum_res<HP4>(hq + row * HP4, s_W + k * HP4, s_w2, on ? sgn : 0);
           const int sg = on ? 1 : -1;
           dhi += sg * (A >> SO_SPLIT_BITS);
           dlo += sg * (int)(A & SO_SPLIT_MASK);
@@ -265,7 +300,7 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
           for (int i = rsub; i < n_list; i += RPP) {
             const unsigned e = s_list[i];
             const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
-            const int4 h = s_hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
+            const int4 h = hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
             ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
             ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
             az += max(h.z + sg * w.z, 0) - max(h.z, 0);
@@ -276,7 +311,7 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
           for (int k = rsub; k < K; k += RPP) {
             const int off = s_off[k];
             const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
-            const int4 h = s_hq[row * HP4 + part], w = s_W[k * HP4 + part];
+            const int4 h = hq[row * HP4 + part], w = s_W[k * HP4 + part];
             ax += max(h.x + sgn * w.x, 0) - max(h.x, 0);
             ay += max(h.y + sgn * w.y, 0) - max(h.y, 0);
             az += max(h.z + sgn * w.z, 0) - max(h.z, 0);
@@ -337,7 +372,7 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
 #pragma unroll 4
           for (int k = rsub; k < K; k += RPP) {
             const int off = s_off[k];
-            int4 *hp = s_hq + (wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d)) * HP4 + part;
+            int4 *hp = hq + (wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d)) * HP4 + part;
             int4 h = *hp;
             const int4 w = s_W[k * HP4 + part];
             h.x += sgn * w.x; h.y += sgn * w.y; h.z += sgn * w.z; h.w += sgn * w.w;
@@ -370,7 +405,8 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
       __syncwarp();
     }
     for (int w = lane; w < W; w += 32) bits_g[w] = s_bits[w];
-    for (int q = lane; q < N * HP4; q += 32) hq_g[q] = s_hq[q];
+    if constexpr (RES)
+      for (int q = lane; q < N * HP4; q += 32) hq_g[q] = s_hq[q];
     if (lane == 0) {
       P.hi[c] = hi;
       P.lo[c] = lo;
@@ -384,14 +420,21 @@ __global__ void __launch_bounds__(512) sa_resident_kernel(SaParams P) {
 
 }  // namespace
 
+static size_t shared_tables_bytes(const so_surrogate *s) {
+  const int n_tree = s->gated ? s->n_tree : 0;
+  return (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4) + (size_t)s->HP4 * 16;
+}
+static bool shape_ok(const so_surrogate *s, int N) {
+  return !((s->gated ? s->n_tree : 0) > 2048 || s->K > 1024 || s->HP4 > 8 || N > 32767);
+}
+
 // Warps per CTA and its shared memory, maximising the resident chains of an SM; false if the state does not fit
 // (or the tree is too large to share).
 bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out) {
   const size_t kSmemSM = 228 * 1024, kSmemCTA = 227 * 1024;
   const int KW = (s->K + 31) / 32;
-  const int n_tree = s->gated ? s->n_tree : 0;
-  if (n_tree > 2048 || s->K > 1024 || s->HP4 > 8 || N > 32767) return false;
-  const size_t shared = (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4) + (size_t)s->HP4 * 16;
+  if (!shape_ok(s, N)) return false;
+  const size_t shared = shared_tables_bytes(s);
   const size_t per_warp = (size_t)N * s->HP4 * 16 + a16((size_t)(2 * W + (s->gated ? N * KW + s->K : 0)) * 4 + (s->gated ? (size_t)s->K * 2 : 0));
   int best_w = 0, best_total = 0;
   size_t best_smem = 0;
@@ -409,6 +452,20 @@ bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_
   return true;
 }
 
+// gated surrogate on a lattice too large for shared memory: can the cached-gate kernel (global state) run it?
+bool so_gate_index_ok(const so_surrogate *s, int N, int W) {
+  if (!s->gated || !shape_ok(s, N)) return false;
+  const size_t per_warp = a16((size_t)(2 * W + s->K) * 4 + (size_t)s->K * 2);
+  return shared_tables_bytes(s) + 8 * per_warp <= 100 * 1024;
+}
+
+#define SO_RES_LAUNCH(V, G, R)                                                                             \
+  {                                                                                                        \
+    auto kern = sa_resident_kernel<V, G, R>;                                                               \
+    SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
+  }
+
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st) {
   const so_surrogate *s = c->sur;
   int n_sm = 0, warps = 0;
@@ -419,18 +476,49 @@ int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_
   long long want = (P.n_chains + warps - 1) / warps;
   int blocks = (int)(want < (long long)n_sm * per_sm ? want : (long long)n_sm * per_sm);
   if (blocks < 1) blocks = 1;
-#define SO_RES_CASE(V)                                                                                       \
-  case V: {                                                                                                  \
-    if (s->gated) {                                                                                          \
-      auto kern = sa_resident_kernel<V, true>;                                                               \
-      SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-      kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
-    } else {                                                                                                 \
-      auto kern = sa_resident_kernel<V, false>;                                                              \
-      SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-      kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
-    }                                                                                                        \
-  } break;
+#define SO_RES_CASE(V) \
+  case V:              \
+    if (s->gated) SO_RES_LAUNCH(V, true, true) else SO_RES_LAUNCH(V, false, true) break;
+  switch (s->HP4) {
+    SO_RES_CASE(1) SO_RES_CASE(2) SO_RES_CASE(3) SO_RES_CASE(4) SO_RES_CASE(5) SO_RES_CASE(6) SO_RES_CASE(7) SO_RES_CASE(8)
+    default: so_set_error("hidden width not supported"); return SO_EINVAL;
+  }
+#undef SO_RES_CASE
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+
+// gated, large lattice: 8 warps per CTA, four CTAs per SM (64 registers per thread: the step is a chain of dependent
+// global loads, occupancy pays more than the spills cost); the path index of each resident
+// warp lives in a scratch buffer of the chains handle
+int so_launch_anneal_gate_index(const so_chains *c, const SaParams &P0, cudaStream_t st) {
+  const so_surrogate *s = c->sur;
+  int n_sm = 0;
+  const int warps = 8;
+  SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+  if (!so_gate_index_ok(s, P0.N, P0.W)) { so_set_error("cached-gate kernel: shape not supported"); return SO_EINVAL; }
+  const int KW = (s->K + 31) / 32;
+  const size_t smem = shared_tables_bytes(s) + warps * a16((size_t)(2 * P0.W + s->K) * 4 + (size_t)s->K * 2);
+  long long want = (P0.n_chains + warps - 1) / warps;
+  int blocks = (int)(want < (long long)n_sm * 4 ? want : (long long)n_sm * 4);
+  if (blocks < 1) blocks = 1;
+  const size_t need = (size_t)blocks * warps * P0.N * KW * 4;
+  if (c->gate_scratch_bytes < need) {
+    if (c->gate_scratch) cudaFree(c->gate_scratch);
+    c->gate_scratch = nullptr;
+    c->gate_scratch_bytes = 0;
+    if (cudaMalloc(&c->gate_scratch, need) != cudaSuccess) {
+      cudaGetLastError();
+      so_set_error("out of device memory for the gate index (%zu bytes)", need);
+      return SO_ENOMEM;
+    }
+    c->gate_scratch_bytes = need;
+  }
+  SaParams P = P0;
+  P.gate_scratch = c->gate_scratch;
+#define SO_RES_CASE(V) \
+  case V:              \
+    SO_RES_LAUNCH(V, true, false) break;
   switch (s->HP4) {
     SO_RES_CASE(1) SO_RES_CASE(2) SO_RES_CASE(3) SO_RES_CASE(4) SO_RES_CASE(5) SO_RES_CASE(6) SO_RES_CASE(7) SO_RES_CASE(8)
     default: so_set_error("hidden width not supported"); return SO_EINVAL;

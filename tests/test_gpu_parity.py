@@ -278,6 +278,48 @@ def test_sa_gated_full_descriptor(eng, variant):
     _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24, variant=variant)
 
 
+def _random_tree(K, depth, seed):
+    rng = np.random.default_rng(seed)
+    feature, thr, left, right, active = [], [], [], [], []
+
+    def node(level):
+        i = len(feature)
+        feature.append(-2); thr.append(0.0); left.append(-1); right.append(-1); active.append(int(rng.random() < 0.6))
+        # uneven depth, plus a few tests that ignore their bit (thr outside [0, 1))
+        if level < depth and (level < 2 or rng.random() < 0.8):
+            feature[i] = int(rng.integers(0, K))
+            thr[i] = float(rng.choice([0.5, 0.5, 0.5, 0.5, -1.0, 1.5]))
+            left[i] = node(level + 1)
+            right[i] = node(level + 1)
+        return i
+    node(0)
+    return dict(feature=np.array(feature, np.int32), thr=np.array(thr), left=np.array(left, np.int32),
+                right=np.array(right, np.int32), active=np.array(active, np.uint8))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("d,T0", [(24, 0.05), (24, 2.0), (40, 0.3)])
+def test_sa_gated_local_large_lattice(eng, d, T0, variant):
+    """Tree gate on a lattice too large for shared memory: the cached-gate kernel (variant 0: gate bits + path index,
+    only active rows read) and the row-per-lane kernel (variant 1) against the oracle; hot runs exercise the index
+    upkeep on accept."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=60 + d)
+    p.tree = _random_tree(49, 7, seed=d)
+    r = _run_sa(eng, d, p, n_chains=20, steps=1500, seed=70 + d, T0=T0, variant=variant,
+                cooling="const" if T0 > 1 else "exp")
+    if T0 > 1:
+        assert r["acc"].mean() > 0.1
+
+
+@pytest.mark.parametrize("d", [8, 12])
+def test_sa_gated_hot_resident(eng, d):
+    """Resident gated kernel at high acceptance (index upkeep every few steps), local window with wraps."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=80 + d)
+    p.tree = _random_tree(49, 8, seed=100 + d)
+    r = _run_sa(eng, d, p, n_chains=24, steps=1500, seed=90 + d, T0=2.0, cooling="const")
+    assert r["acc"].mean() > 0.1
+
+
 def test_sa_kernel_variants_agree(eng):
     """resident == window (pipelined) == generic flat == row-per-lane kernels, bit for bit."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
