@@ -178,6 +178,36 @@ int so_exchange(so_chains *c, int rank, int world, int ladder, int parity, uint6
                 double t_ref, const double *of_all_dev, double *tscale_all_dev, void *stream,
                 int64_t *n_swapped);
 
+/* ---- regressor training on the device (replaces MLPRegressor(...).fit of OML/train_surrogate.py:141-152) ----------
+ * The K -> H -> 1 ReLU MLP fitted by mini-batch Adam exactly as scikit-learn runs it (squared loss / 2 +
+ * alpha / 2 |coefs|^2 / batch; one Adam step per batch; stop when the epoch loss has not improved by tol for more than
+ * n_iter_no_change epochs), fp64, whole optimiser state in the shared memory of one persistent CTA.
+ *   X [n_rows][K] 0/1 descriptor rows (anything else: SO_EINVAL), y [n_rows] scaled targets, W1 [K][H] / b1 [H] /
+ *   w2 [H] / b2 initial parameters (e.g. sklearn's Glorot draws).  so_trainer_run() advances n_epochs epochs (or until
+ *   the stop rule fires); orders [n_epochs][n_rows] is the sample order of each epoch (batches are consecutive slices
+ *   of batch_size), loss_out [n_epochs] receives the epoch losses (0 for epochs not run).                          */
+typedef struct so_trainer so_trainer;
+typedef struct so_train_params {
+  double lr, alpha, beta1, beta2, eps, tol; /* sklearn: learning_rate_init, alpha, beta_1, beta_2, epsilon, tol */
+  int batch_size;                           /* sklearn 'auto' = min(200, n_rows); clipped to n_rows              */
+  int n_iter_no_change;                     /* sklearn default 10                                                */
+} so_train_params;
+typedef struct so_train_status {
+  int epochs_done;      /* epochs run by this call                     */
+  int n_iter;           /* epochs run in total (sklearn n_iter_)        */
+  int stopped;          /* the tol rule has fired                       */
+  int64_t adam_steps;   /* optimiser steps so far (sklearn _optimizer.t) */
+  double best_loss;
+  float kernel_ms;
+} so_train_status;
+int so_trainer_create(int device, int64_t n_rows, int K, int H, const uint8_t *X, const double *y, const double *W1,
+                      const double *b1, const double *w2, double b2, const so_train_params *hp, so_trainer **out);
+int so_trainer_destroy(so_trainer *t);
+int so_trainer_run(so_trainer *t, int n_epochs, const int32_t *orders, double *loss_out, so_train_status *status);
+int so_trainer_get(so_trainer *t, double *W1, double *b1, double *w2, double *b2);
+/* MLPRegressor.predict with the current parameters: X [n][K] 0/1 rows -> out [n] (scaled units, fp64) */
+int so_trainer_predict(so_trainer *t, int64_t n, const uint8_t *X, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,16 @@ class AnnealStats(C.Structure):
                 ("kernel_ms", C.c_float)]
 
 
+class TrainParams(C.Structure):
+    _fields_ = [("lr", C.c_double), ("alpha", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("tol", C.c_double), ("batch_size", C.c_int), ("n_iter_no_change", C.c_int)]
+
+
+class TrainStatus(C.Structure):
+    _fields_ = [("epochs_done", C.c_int), ("n_iter", C.c_int), ("stopped", C.c_int), ("adam_steps", C.c_int64),
+                ("best_loss", C.c_double), ("kernel_ms", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/so_b200.h
 PROTOTYPES = {
     "so_version": (C.c_int, []),
@@ -70,6 +80,12 @@ PROTOTYPES = {
     "so_objectives_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "so_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_double,
                               C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
+    "so_trainer_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p, c_f64p, c_f64p, c_f64p, c_f64p,
+                                    C.c_double, C.POINTER(TrainParams), C.POINTER(C.c_void_p)]),
+    "so_trainer_destroy": (C.c_int, [C.c_void_p]),
+    "so_trainer_run": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_f64p, C.POINTER(TrainStatus)]),
+    "so_trainer_get": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "so_trainer_predict": (C.c_int, [C.c_void_p, C.c_int64, c_u8p, c_f64p]),
 }
 
 _lib = None

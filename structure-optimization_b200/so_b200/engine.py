@@ -326,3 +326,69 @@ class Chains(object):
             self.close()
         except Exception:
             pass
+
+
+class Trainer(object):
+    """Device-side Adam fit of the K -> H -> 1 ReLU regressor (so_trainer_*; OML/train_surrogate.py:141-152)."""
+
+    def __init__(self, X, y, W1, b1, w2, b2, lr=1e-4, alpha=0.1, beta1=0.9, beta2=0.999, eps=1e-8, tol=1e-5,
+                 batch_size=None, n_iter_no_change=10, device=0):
+        self.lib = B.load()
+        X = np.asarray(X)
+        if X.ndim != 2:
+            raise ValueError("X must be [n_rows, K]")
+        Xu = np.ascontiguousarray(X, dtype=np.uint8)
+        if not np.array_equal(Xu, X):
+            raise ValueError("training rows must be 0/1 occupancies")
+        self.n_rows, self.K = Xu.shape
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        W1 = np.ascontiguousarray(W1, dtype=np.float64)
+        self.H = W1.shape[1]
+        b1 = np.ascontiguousarray(b1, dtype=np.float64).reshape(-1)
+        w2 = np.ascontiguousarray(w2, dtype=np.float64).reshape(-1)
+        if y.shape != (self.n_rows,) or W1.shape != (self.K, self.H) or b1.shape != (self.H,) or w2.shape != (self.H,):
+            raise ValueError("inconsistent shapes")
+        hp = B.TrainParams(float(lr), float(alpha), float(beta1), float(beta2), float(eps), float(tol),
+                           int(min(200, self.n_rows) if batch_size is None else np.clip(batch_size, 1, self.n_rows)),
+                           int(n_iter_no_change))
+        self.batch_size = hp.batch_size
+        self.h = C.c_void_p()
+        B.check(self.lib.so_trainer_create(int(device), self.n_rows, self.K, self.H, _p(Xu, B.c_u8p), _p(y, B.c_f64p),
+                                           _p(W1, B.c_f64p), _p(b1, B.c_f64p), _p(w2, B.c_f64p), float(b2), C.byref(hp),
+                                           C.byref(self.h)))
+
+    def run(self, orders):
+        """Advance one epoch per row of `orders` [n_epochs, n_rows]; returns (epoch losses actually run, status dict)."""
+        orders = np.ascontiguousarray(orders, dtype=np.int32).reshape(-1, self.n_rows)
+        loss = np.zeros(len(orders))
+        st = B.TrainStatus()
+        B.check(self.lib.so_trainer_run(self.h, len(orders), _p(orders, B.c_i32p), _p(loss, B.c_f64p), C.byref(st)))
+        return loss[:st.epochs_done], dict(epochs_done=st.epochs_done, n_iter=st.n_iter, stopped=bool(st.stopped),
+                                           adam_steps=st.adam_steps, best_loss=st.best_loss, kernel_ms=st.kernel_ms)
+
+    def predict(self, X):
+        Xu = np.ascontiguousarray(X, dtype=np.uint8).reshape(-1, self.K)
+        if not np.array_equal(Xu, np.asarray(X).reshape(-1, self.K)):
+            raise ValueError("rows must be 0/1 occupancies")
+        out = np.empty(len(Xu))
+        B.check(self.lib.so_trainer_predict(self.h, len(Xu), _p(Xu, B.c_u8p), _p(out, B.c_f64p)))
+        return out
+
+    def get(self):
+        W1 = np.empty((self.K, self.H))
+        b1 = np.empty(self.H)
+        w2 = np.empty(self.H)
+        b2 = C.c_double()
+        B.check(self.lib.so_trainer_get(self.h, _p(W1, B.c_f64p), _p(b1, B.c_f64p), _p(w2, B.c_f64p), C.byref(b2)))
+        return W1, b1, w2, b2.value
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.so_trainer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

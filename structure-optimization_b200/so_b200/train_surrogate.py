@@ -1,6 +1,7 @@
 """
-surrogate -- drop-in for OML/train_surrogate.py:15-184.  Training stays on the host with scikit-learn (the weights'
-source named by the task); the evaluate side (eval_structure_rate, called `eval_rate` by optimize()) runs on the GPU.
+surrogate -- drop-in for OML/train_surrogate.py:15-184.  The regressor is fitted on the GPU by default (DeviceMLPRegressor: scikit-learn's Adam
+recipe restated in so_train.cu; `on_device=False` calls scikit-learn itself), the tree classifier and the Y scaler
+stay scikit-learn's; the evaluate side (eval_structure_rate, called `eval_rate` by optimize()) runs on the GPU.
 Upstream defects resolved as in SURVEY 9.5: `Y_scaler` is stored, `train` takes self, both method names exist.
 """
 import numpy as np
@@ -39,6 +40,92 @@ def tables_for(surr, lattice, gate=True):
     return engine.SurrogateTables(lattice, descriptor_offsets(W1.shape[0], lattice.d), W1, mlp.intercepts_[0],
                                   np.asarray(mlp.coefs_[1]).reshape(-1), float(np.asarray(mlp.intercepts_[1]).reshape(-1)[0]),
                                   y_mean, y_scale, flatten_tree(clf) if clf is not None else None)
+
+
+class DeviceMLPRegressor(object):
+    """The MLPRegressor of OML/train_surrogate.py:150-151 fitted on the GPU (so_trainer_*): scikit-learn's mini-batch
+    Adam with L2 penalty, its Glorot initialisation and its epoch shuffles drawn from the same `random_state`, so a
+    fit reproduces `sklearn.neural_network.MLPRegressor(...).fit` to rounding.  Exposes the fitted attributes the
+    reference and tables_for() read (coefs_, intercepts_, out_activation_, loss_curve_, n_iter_, best_loss_)."""
+
+    out_activation_ = 'identity'
+
+    def __init__(self, hidden_layer_sizes=(20,), activation='relu', learning_rate_init=0.001, alpha=0.0001,
+                 max_iter=200, tol=1e-4, random_state=None, verbose=False, batch_size='auto', beta_1=0.9, beta_2=0.999,
+                 epsilon=1e-8, n_iter_no_change=10, device=0, epochs_per_launch=16):
+        if activation != 'relu' or len(tuple(hidden_layer_sizes)) != 1:
+            raise ValueError('the device trainer fits the single-hidden-layer ReLU regressor of train_surrogate.py')
+        self.hidden_layer_sizes = tuple(hidden_layer_sizes)
+        self.learning_rate_init, self.alpha, self.max_iter, self.tol = learning_rate_init, alpha, max_iter, tol
+        self.random_state, self.verbose, self.batch_size = random_state, verbose, batch_size
+        self.beta_1, self.beta_2, self.epsilon, self.n_iter_no_change = beta_1, beta_2, epsilon, n_iter_no_change
+        self._device, self._chunk = device, int(epochs_per_launch)
+        self._trainer = None
+
+    @staticmethod
+    def _rng(random_state):
+        if random_state is None:
+            return np.random.mtrand._rand                  # sklearn.utils.check_random_state(None)
+        if isinstance(random_state, np.random.RandomState):
+            return random_state
+        return np.random.RandomState(random_state)
+
+    def fit(self, X, y):
+        X = np.asarray(X)
+        y = np.asarray(y, dtype=np.float64).reshape(-1)
+        n, K = X.shape
+        H = int(self.hidden_layer_sizes[0])
+        rng = self._rng(self.random_state)
+        # sklearn _init_coef: Glorot uniform, draws in the order coef 0, intercept 0, coef 1, intercept 1
+        b = np.sqrt(6.0 / (K + H))
+        W1 = rng.uniform(-b, b, (K, H))
+        b1 = rng.uniform(-b, b, H)
+        b = np.sqrt(6.0 / (H + 1))
+        w2 = rng.uniform(-b, b, (H, 1)).reshape(-1)
+        b2 = float(rng.uniform(-b, b, 1)[0])
+        if self._trainer is not None:
+            self._trainer.close()
+        self._trainer = engine.Trainer(X, y, W1, b1, w2, b2, lr=self.learning_rate_init, alpha=self.alpha,
+                                       beta1=self.beta_1, beta2=self.beta_2, eps=self.epsilon, tol=self.tol,
+                                       batch_size=None if self.batch_size == 'auto' else self.batch_size,
+                                       n_iter_no_change=self.n_iter_no_change, device=self._device)
+        sample_idx = np.arange(n)
+        curve, status, self.kernel_ms_ = [], dict(stopped=False, n_iter=0, best_loss=np.inf), 0.0
+        while len(curve) < self.max_iter and not status['stopped']:
+            m = min(self._chunk, self.max_iter - len(curve))
+            orders = np.empty((m, n), dtype=np.int32)
+            for e in range(m):                              # sklearn.utils.shuffle(sample_idx, random_state=rng)
+                perm = np.arange(n)
+                rng.shuffle(perm)
+                sample_idx = sample_idx[perm]
+                orders[e] = sample_idx
+            loss, status = self._trainer.run(orders)
+            self.kernel_ms_ += status['kernel_ms']
+            curve.extend(loss.tolist())
+            if self.verbose:
+                for i, v in enumerate(loss):
+                    print('Iteration %d, loss = %.8f' % (len(curve) - len(loss) + i + 1, v))
+        self.loss_curve_, self.n_iter_ = curve, status['n_iter']
+        self.loss_, self.best_loss_ = (curve[-1] if curve else np.inf), status['best_loss']
+        self.t_ = self.n_iter_ * n
+        W1, b1, w2, b2 = self._trainer.get()
+        self.coefs_ = [W1, w2.reshape(-1, 1)]
+        self.intercepts_ = [b1, np.array([b2])]
+        self.n_layers_, self.n_outputs_ = 3, 1
+        if not status['stopped']:
+            import warnings
+            try:
+                from sklearn.exceptions import ConvergenceWarning as _Warn
+            except Exception:
+                _Warn = UserWarning
+            warnings.warn("Stochastic Optimizer: Maximum iterations (%d) reached and the optimization hasn't "
+                          "converged yet." % self.max_iter, _Warn)
+        return self
+
+    def predict(self, X):
+        if self._trainer is None:
+            raise RuntimeError('this DeviceMLPRegressor is not fitted yet')
+        return self._trainer.predict(np.asarray(X))
 
 
 class surrogate(object):
@@ -83,11 +170,12 @@ class surrogate(object):
         return np.where(active, rate, 0.0)
 
     # ---- train (host, scikit-learn; OML/train_surrogate.py:61-152) --------------------------------------------
-    def train(self, structure_occs, site_rates, curr_fldr=None, max_iter=10000, random_state=None, verbose=False):
+    def train(self, structure_occs, site_rates, curr_fldr=None, max_iter=10000, random_state=None, verbose=False,
+              on_device=True):
         self.all_syms = np.asarray(structure_occs)
         self.partition_data_set(np.asarray(site_rates))
         self.train_classifier()
-        self.train_regressor(max_iter=max_iter, random_state=random_state, verbose=verbose)
+        self.train_regressor(max_iter=max_iter, random_state=random_state, verbose=verbose, on_device=on_device)
         self._tables = None
 
     def partition_data_set(self, site_rates):
@@ -108,15 +196,21 @@ class surrogate(object):
         self.frac_wrong_train = float(np.sum(np.abs(self.classifier.predict(X_train) - y_train))) / len(y_train)
         self.frac_wrong_test = float(np.sum(np.abs(self.classifier.predict(X_test) - y_test))) / len(y_test)
 
-    def train_regressor(self, reg_parity_fname=None, max_iter=10000, random_state=None, verbose=False):
-        from sklearn.neural_network import MLPRegressor
+    def train_regressor(self, reg_parity_fname=None, max_iter=10000, random_state=None, verbose=False, on_device=True):
+        """OML/train_surrogate.py:141-152.  on_device=True fits the same model with the same optimiser on the GPU
+        (DeviceMLPRegressor); on_device=False calls scikit-learn itself, as the reference does."""
         from sklearn.preprocessing import StandardScaler
         self.Y_scaler = StandardScaler(with_mean=True, with_std=True)
         self.Y_scaler.fit(self.Y_reg.reshape(-1, 1))
         Y = self.Y_scaler.transform(self.Y_reg.reshape(-1, 1)).flatten()
-        self.predictor = MLPRegressor(activation='relu', verbose=verbose, learning_rate_init=0.0001, alpha=0.1,
-                                      hidden_layer_sizes=(20,), max_iter=max_iter, tol=0.00001,
-                                      random_state=random_state)
+        if on_device:
+            Regressor, extra = DeviceMLPRegressor, dict(device=self._device)
+        else:
+            from sklearn.neural_network import MLPRegressor as Regressor
+            extra = {}
+        self.predictor = Regressor(activation='relu', verbose=verbose, learning_rate_init=0.0001, alpha=0.1,
+                                   hidden_layer_sizes=(20,), max_iter=max_iter, tol=0.00001,
+                                   random_state=random_state, **extra)
         self.predictor.fit(self.X_reg, Y)
         pred = self.Y_scaler.inverse_transform(self.predictor.predict(self.X_reg).reshape(-1, 1)).flatten()
         self.mean_abs_error = float(np.mean(np.abs(pred - self.Y_reg)))
