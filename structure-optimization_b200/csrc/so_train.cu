@@ -2,15 +2,20 @@
 // OML/train_surrogate.py:141-152, mini-batch Adam with L2 penalty exactly as scikit-learn's MLPRegressor runs it
 // (squared loss / 2, alpha / 2 |coefs|^2 / batch, one Adam step per batch, tol-based stop on the epoch loss), in fp64.
 //
-// Training is a strictly sequential chain of tiny batches (200 rows x K x H: ~1 M fp64 FMA per step, up to ~1e6
-// steps), so the whole optimiser state lives in the shared memory of ONE persistent CTA: weights, both Adam moments,
-// the batch's activations and its rows as bit-vectors (inputs are 0/1 occupancies: the first layer is a sum of weight
-// rows over set bits, its gradient a masked sum over the batch).  Nothing but the batch rows (K/8 B each) and the
-// targets is read from HBM per step.  The order of the samples in every epoch is supplied by the caller, so a run
-// can replay scikit-learn's own shuffles (parity tests) or any other stream.
+// Training is a strictly sequential chain of tiny batches (200 rows x K x H: ~0.6 M fp64 additions per step after
+// exploiting the 0/1 inputs, up to ~1e6 steps), so it runs as ONE persistent thread-block cluster of 8 CTAs with the
+// whole optimiser state in (distributed) shared memory: every CTA keeps a replica of the parameters and works on an
+// eighth of each batch's rows (rows as bit-vectors: the first layer is a sum of weight rows over set bits, its gradient
+// a sum of delta rows over the set bits of the ballot-transposed batch); the gradients are reduce-scattered through
+// DSMEM, each CTA applies Adam to the parameter slice whose moments it owns and stores the result into all replicas.
+// Nothing but the batch rows (K/8 B each) and the targets is read from HBM per step.  The order of the samples in every
+// epoch is supplied by the caller, so a run can replay scikit-learn's own shuffles (parity tests) or any other stream.
 #include "so_internal.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
+
+namespace cg = cooperative_groups;
 
 #define SO_REQUIRE(cond, ...)        \
   do {                               \
@@ -49,150 +54,295 @@ struct so_trainer {
 namespace {
 
 constexpr int TRAIN_THREADS = 1024;
+constexpr int TRAIN_CTAS = 8;            // one thread-block cluster
+constexpr int TRAIN_MAX_BATCH = 1024;    // <= 128 rows per CTA (four row words)
 
-__device__ __forceinline__ double block_sum(double v, double *scratch) {
+// block-wide sums of two values at once; results in scratch[32] and scratch[36]
+__device__ __forceinline__ void block_sum2(double v, double w, double *scratch) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SO_FULL, v, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(SO_FULL, v, o);
+    w += __shfl_xor_sync(SO_FULL, w, o);
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __syncthreads();
-  if (lane == 0) scratch[warp] = v;
+  if (lane == 0) { scratch[warp] = v; scratch[40 + warp] = w; }
   __syncthreads();
   if (warp == 0) {
     v = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.0;
+    w = lane < (int)(blockDim.x >> 5) ? scratch[40 + lane] : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SO_FULL, v, o);
-    if (lane == 0) scratch[32] = v;
+    for (int o = 16; o > 0; o >>= 1) {
+      v += __shfl_xor_sync(SO_FULL, v, o);
+      w += __shfl_xor_sync(SO_FULL, w, o);
+    }
+    if (lane == 0) { scratch[32] = v; scratch[36] = w; }
   }
   __syncthreads();
-  return scratch[32];
 }
 
-// parameter vector: [ (K+1)*H : W1 rows 0..K-1, then b1 as row K ][ H : w2 ][ 1 : b2 ]
-__global__ void __launch_bounds__(TRAIN_THREADS, 1)
+struct TrainLayout {       // shared memory of one CTA, in doubles unless noted
+  int P1, P, slice0, slice1, rows_max, RW;
+  size_t th, gp, mo, ve, act, d2, misc, xb, xt, bytes;
+};
+__host__ __device__ inline TrainLayout train_layout(int K, int H, int batch, int rank) {
+  TrainLayout L;
+  L.P1 = (K + 1) * H;
+  L.P = L.P1 + H + 1;
+  L.slice0 = (int)((long long)L.P * rank / TRAIN_CTAS);
+  L.slice1 = (int)((long long)L.P * (rank + 1) / TRAIN_CTAS);
+  L.rows_max = (batch + TRAIN_CTAS - 1) / TRAIN_CTAS;
+  L.RW = (L.rows_max + 31) / 32;
+  const int KW = (K + 31) / 32;
+  const int slice_max = L.P / TRAIN_CTAS + 1;
+  size_t o = 0;
+  L.th = o; o += L.P;                        // all parameters (replica)
+  L.gp = o; o += L.P;                        // this CTA's partial gradients; [P] = its sum of squared residuals,
+  o += 2;                                    // [P + 1] = sum of squares of the coefficients in its slice
+  L.mo = o; o += slice_max;                  // Adam moments of this CTA's parameter slice
+  L.ve = o; o += slice_max;
+  L.act = o; o += (size_t)L.rows_max * H;    // activations, then delta1, of this CTA's rows
+  L.d2 = o; o += L.rows_max;
+  L.misc = o; o += 72;                       // block reduction scratch [0..32], [36], [40..71]; lr_t [33], [35]; stop flag [34]
+  L.xb = o * 8; o += ((size_t)L.rows_max * KW + 1) / 2;      // u32 [rows][KW]
+  L.xt = o * 8; o += ((size_t)(K + 1) * L.RW + 1) / 2;       // u32 [K + 1][RW]: column k as a bit mask over the rows
+  L.bytes = o * 8 + 16;
+  return L;
+}
+
+// One cluster of 8 CTAs runs the whole optimisation.  Each CTA holds a replica of the parameters, takes 1/8 of the
+// rows of every batch (forward, residuals, partial gradients over its rows), then the cluster reduce-scatters the
+// gradients through distributed shared memory: CTA c sums the eight partials of its parameter slice in rank order,
+// applies Adam with the moments it owns and stores the new values into all eight replicas.  Two cluster barriers per
+// batch.  parameter vector: [ (K+1)*H : W1 rows 0..K-1, then b1 as row K ][ H : w2 ][ 1 : b2 ]
+__global__ void __cluster_dims__(TRAIN_CTAS, 1, 1) __launch_bounds__(TRAIN_THREADS, 1)
     train_kernel(int K, int KW, int H, int batch, long long n_rows, const uint32_t *__restrict__ xbits,
                  const double *__restrict__ y, double *theta_g, TrainState *state_g, int n_epochs,
                  const int32_t *__restrict__ orders, double *loss_out, double lr, double alpha, double beta1, double beta2,
                  double eps, double tol, int n_iter_no_change) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  const int P1 = (K + 1) * H, P = P1 + H + 1;
-  double *th = (double *)s_raw;            // parameters
-  double *mo = th + P;                     // first moment
-  double *ve = mo + P;                     // second moment
-  double *act = ve + P;                    // [batch][H] activations, then delta1
-  double *d2 = act + (size_t)batch * H;    // [batch]
-  double *gw2 = d2 + batch;                // [H + 1] gradients of w2, b2
-  double *scratch = gw2 + H + 1;           // [34]: block reduction + lr_t
-  uint32_t *xb = (uint32_t *)(scratch + 34);   // [batch][KW]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const TrainLayout L = train_layout(K, H, batch, rank);
+  const int P1 = L.P1, P = L.P, RW = L.RW;
+  double *base = (double *)s_raw;
+  double *th = base + L.th, *gp = base + L.gp, *mo = base + L.mo, *ve = base + L.ve, *act = base + L.act;
+  double *d2 = base + L.d2, *misc = base + L.misc;
+  uint32_t *xb = (uint32_t *)(s_raw + L.xb), *xt = (uint32_t *)(s_raw + L.xt);
   __shared__ TrainState st;
-  __shared__ int s_stop;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double *gp_of[TRAIN_CTAS];
+  double *th_of[TRAIN_CTAS];
+#pragma unroll
+  for (int c = 0; c < TRAIN_CTAS; ++c) {
+    gp_of[c] = cluster.map_shared_rank(gp, c);
+    th_of[c] = cluster.map_shared_rank(th, c);
+  }
 
-  for (int i = tid; i < 3 * P; i += blockDim.x) th[i] = theta_g[i];
-  if (tid == 0) { st = *state_g; s_stop = st.stopped; }
+  for (int i = tid; i < P; i += blockDim.x) th[i] = theta_g[i];
+  for (int i = L.slice0 + tid; i < L.slice1; i += blockDim.x) {
+    mo[i - L.slice0] = theta_g[P + i];
+    ve[i - L.slice0] = theta_g[2 * P + i];
+  }
+  if (tid == 0) { st = *state_g; misc[34] = st.stopped ? 1.0 : 0.0; }
   __syncthreads();
+  cluster.sync();
 
-  for (int e = 0; e < n_epochs && !s_stop; ++e) {
+  // the rows of the NEXT batch travel in registers while the current one is processed (order -> row: two dependent
+  // global round trips per batch otherwise)
+  constexpr int EPT = 4;
+  const bool prefetch = L.rows_max * KW <= EPT * (int)blockDim.x;
+  uint32_t px[EPT];
+  double py = 0.0;
+  auto fetch = [&](int e2, long long s02) {
+    const int32_t *order2 = orders + (size_t)e2 * n_rows;
+    const int nb2 = (int)min((long long)batch, n_rows - s02);
+    const int lo2 = (int)((long long)nb2 * rank / TRAIN_CTAS), nr2 = (int)((long long)nb2 * (rank + 1) / TRAIN_CTAS) - lo2;
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int i = tid + u * (int)blockDim.x;
+      if (i < nr2 * KW) {
+        const int r = i / KW, w = i - r * KW;
+        px[u] = xbits[(size_t)order2[s02 + lo2 + r] * KW + w];
+      }
+    }
+    if (tid < nr2) py = y[order2[s02 + lo2 + tid]];
+  };
+  // beta^t as running products (pow() once per launch: a per-step pow on one thread stalled every barrier behind it)
+  long long t = st.t;
+  double b1t = pow(beta1, (double)t), b2t = pow(beta2, (double)t);
+  if (prefetch && n_epochs > 0 && misc[34] == 0.0) fetch(0, 0);
+
+  for (int e = 0; e < n_epochs && misc[34] == 0.0; ++e) {
     const int32_t *order = orders + (size_t)e * n_rows;
-    double acc_loss = 0.0;                 // thread 0 only
+    double acc_loss = 0.0;                 // rank 0, thread 0 only
     for (long long s0 = 0; s0 < n_rows; s0 += batch) {
       const int nb = (int)min((long long)batch, n_rows - s0);
-      const double inv_nb = 1.0 / (double)nb;
-      // ---- batch rows (bit-vectors) and targets ----
-      for (int i = tid; i < nb * KW; i += blockDim.x) {
-        const int r = i / KW, w = i - r * KW;
-        xb[i] = xbits[(size_t)order[s0 + r] * KW + w];
-      }
-      if (tid < nb) d2[tid] = y[order[s0 + tid]];
-      if (tid == 0) {
-        st.t += 1;
-        scratch[33] = lr * sqrt(1.0 - pow(beta2, (double)st.t)) / (1.0 - pow(beta1, (double)st.t));
+      const int r_lo = (int)((long long)nb * rank / TRAIN_CTAS), r_hi = (int)((long long)nb * (rank + 1) / TRAIN_CTAS);
+      const int nr = r_hi - r_lo;          // this CTA's rows of the batch
+      t += 1;
+      b1t *= beta1;
+      b2t *= beta2;
+      // ---- rows (bit-vectors) and targets ----
+      if (prefetch) {
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+          const int i = tid + u * (int)blockDim.x;
+          if (i < nr * KW) xb[i] = px[u];
+        }
+        if (tid < nr) d2[tid] = py;
+      } else {
+        for (int i = tid; i < nr * KW; i += blockDim.x) {
+          const int r = i / KW, w = i - r * KW;
+          xb[i] = xbits[(size_t)order[s0 + r_lo + r] * KW + w];
+        }
+        if (tid < nr) d2[tid] = y[order[s0 + r_lo + tid]];
       }
       __syncthreads();
+      if (prefetch) {
+        if (s0 + batch < n_rows) fetch(e, s0 + batch);
+        else if (e + 1 < n_epochs) fetch(e + 1, 0);
+      }
+      // ---- columns as bit masks over the rows (ballot transpose); column K = all rows (bias) ----
+      for (int i = warp; i < (K + 1) * RW; i += (int)(blockDim.x >> 5)) {
+        const int k = i / RW, q = i - k * RW, r = 32 * q + lane;
+        const unsigned bit = r < nr ? (k < K ? (xb[r * KW + (k >> 5)] >> (k & 31)) & 1u : 1u) : 0u;
+        const unsigned m = __ballot_sync(SO_FULL, bit);
+        if (lane == 0) xt[i] = m;
+      }
       // ---- forward, first layer: a[r][j] = relu(b1[j] + sum over set bits k of W1[k][j]) ----
-      for (int p = tid; p < nb * H; p += blockDim.x) {
-        const int r = p / H, j = p - r * H;
-        double h = th[K * H + j];
-        for (int w = 0; w < KW; ++w) {
-          uint32_t bits = xb[r * KW + w];
-          const double *row = th + (size_t)(32 * w) * H + j;
-          while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            h += row[k * H];
+      // (two adjacent lanes per (row, unit): each sums half of the row's words, so the dependent chains are half as long)
+      {
+        const int KWh = (KW + 1) >> 1, n_slots = 2 * nr * H;
+        for (int q0 = 0; q0 < n_slots; q0 += blockDim.x) {
+          const int q = q0 + tid, p = q >> 1;
+          double h0 = 0.0, h1 = 0.0;
+          int r = 0, j = 0;
+          if (q < n_slots) {
+            r = p / H;
+            j = p - r * H;
+            const int w_lo = (q & 1) ? KWh : 0, w_hi = (q & 1) ? KW : KWh;
+            for (int w = w_lo; w < w_hi; ++w) {
+              // set bits only: half the shared-memory traffic of a predicated sweep over all positions, which measured
+              // slower (the loop is bound by LDS.64 bandwidth and issue together)
+              uint32_t bits = xb[r * KW + w];
+              const double *row = th + (size_t)(32 * w) * H + j;
+              while (bits) {
+                const int k0 = __ffs(bits) - 1;
+                bits &= bits - 1;
+                h0 += row[k0 * H];
+                if (bits) {
+                  const int k1 = __ffs(bits) - 1;
+                  bits &= bits - 1;
+                  h1 += row[k1 * H];
+                }
+              }
+            }
           }
+          h0 += h1;
+          const double other = __shfl_xor_sync(SO_FULL, h0, 1);
+          if (q < n_slots && !(q & 1)) act[p] = fmax(th[K * H + j] + h0 + other, 0.0);
         }
-        act[p] = fmax(h, 0.0);
       }
       __syncthreads();
       // ---- output, residual, loss terms ----
       double part = 0.0;
-      if (tid < nb) {
+      if (tid < nr) {
         double pred = th[P1 + H];
         for (int j = 0; j < H; ++j) pred += act[tid * H + j] * th[P1 + j];
         const double dd = pred - d2[tid];
         d2[tid] = dd;
         part = dd * dd;
       }
-      const double sq = block_sum(part, scratch);
-      part = 0.0;
-      for (int i = tid; i < K * H; i += blockDim.x) part += th[i] * th[i];
-      if (tid < H) part += th[P1 + tid] * th[P1 + tid];
-      const double wsq = block_sum(part, scratch);
-      if (tid == 0) acc_loss += (0.5 * sq * inv_nb + 0.5 * alpha * wsq * inv_nb) * nb;
-      // ---- gradients of the output layer (warp j: column j of a^T delta2; warp H: sum of delta2) ----
+      double part2 = 0.0;                  // squares of the coefficients (not intercepts) of this CTA's slice
+      for (int p = L.slice0 + tid; p < L.slice1; p += blockDim.x)
+        if (p < K * H || (p >= P1 && p < P1 + H)) part2 += th[p] * th[p];
+      block_sum2(part, part2, misc);
+      if (tid == 0) { gp[P] = misc[32]; gp[P + 1] = misc[36]; }
+      // ---- partial gradients of the output layer (warp j: column j of a^T delta2; warp H: sum of delta2) ----
       if (warp <= H) {
         double g = 0.0;
-        for (int r = lane; r < nb; r += 32) g += (warp < H ? act[r * H + warp] : 1.0) * d2[r];
+        for (int r = lane; r < nr; r += 32) g += (warp < H ? act[r * H + warp] : 1.0) * d2[r];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(SO_FULL, g, o);
-        if (lane == 0) gw2[warp] = warp < H ? (g + alpha * th[P1 + warp]) / (double)nb : g / (double)nb;
+        if (lane == 0) gp[P1 + warp] = g;
       }
       __syncthreads();
-      // ---- delta1 in place of the activations (old w2) ----
-      for (int p = tid; p < nb * H; p += blockDim.x) {
+      // ---- delta1 in place of the activations ----
+      for (int p = tid; p < nr * H; p += blockDim.x) {
         const int r = p / H, j = p - r * H;
         act[p] = act[p] > 0.0 ? d2[r] * th[P1 + j] : 0.0;
       }
       __syncthreads();
-      // ---- first-layer gradients + Adam, one parameter per thread slot; then the output layer's parameters ----
-      const double lr_t = scratch[33];
-      for (int p = tid; p < P; p += blockDim.x) {
-        double g;
-        if (p < P1) {
-          const int k = p / H, j = p - k * H;
-          g = 0.0;
-          if (k < K) {
-            const int w = k >> 5, sh = k & 31;
-            for (int r = 0; r < nb; ++r)
-              if ((xb[r * KW + w] >> sh) & 1u) g += act[r * H + j];
-            g = (g + alpha * th[p]) / (double)nb;
-          } else {                                   // b1: no penalty
-            for (int r = 0; r < nb; ++r) g += act[r * H + j];
-            g /= (double)nb;
+      // ---- partial first-layer gradients: sum of delta1 over the rows that have column k set ----
+      for (int p = tid; p < P1; p += blockDim.x) {
+        const int k = p / H, j = p - k * H;
+        double g0 = 0.0, g1 = 0.0;
+        for (int q = 0; q < RW; ++q) {
+          uint32_t bits = xt[k * RW + q];
+          const double *col = act + (size_t)(32 * q) * H + j;
+          while (bits) {
+            const int r0 = __ffs(bits) - 1;
+            bits &= bits - 1;
+            g0 += col[r0 * H];
+            if (bits) {
+              const int r1 = __ffs(bits) - 1;
+              bits &= bits - 1;
+              g1 += col[r1 * H];
+            }
           }
-        } else {
-          g = gw2[p - P1];
         }
-        const double m = beta1 * mo[p] + (1.0 - beta1) * g;
-        const double v = beta2 * ve[p] + (1.0 - beta2) * (g * g);
-        mo[p] = m;
-        ve[p] = v;
-        th[p] += -lr_t * m / (sqrt(v) + eps);
+        gp[p] = g0 + g1;
       }
-      __syncthreads();
+      cluster.sync();                      // all partial gradients are in place
+      // ---- reduce-scatter + Adam on this CTA's slice; new values go to every replica ----
+      const double lr_t = lr * sqrt(1.0 - b2t) / (1.0 - b1t);
+      for (int p = L.slice0 + tid; p < L.slice1; p += blockDim.x) {
+        double g = 0.0;
+#pragma unroll
+        for (int c = 0; c < TRAIN_CTAS; ++c) g += gp_of[c][p];
+        if (p < K * H || (p >= P1 && p < P1 + H)) g += alpha * th[p];      // L2 penalty on the coefficients only
+        g /= (double)nb;
+        const int q = p - L.slice0;
+        const double m = beta1 * mo[q] + (1.0 - beta1) * g;
+        const double v = beta2 * ve[q] + (1.0 - beta2) * (g * g);
+        mo[q] = m;
+        ve[q] = v;
+        const double nv = th[p] + -lr_t * m / (sqrt(v) + eps);
+#pragma unroll
+        for (int c = 0; c < TRAIN_CTAS; ++c) th_of[c][p] = nv;
+      }
+      if (rank == 0 && tid == 0) {
+        double sq_all = 0.0, wsq = 0.0;
+#pragma unroll
+        for (int c = 0; c < TRAIN_CTAS; ++c) {
+          sq_all += gp_of[c][P];
+          wsq += gp_of[c][P + 1];
+        }
+        acc_loss += (0.5 * sq_all / (double)nb + 0.5 * alpha * wsq / (double)nb) * nb;
+      }
+      cluster.sync();                      // every replica holds the new parameters; partials may be overwritten
     }
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
       const double cur = acc_loss / (double)n_rows;
       loss_out[e] = cur;
       st.n_iter += 1;
       st.count = cur > st.best - tol ? st.count + 1 : 0;
       if (cur < st.best) st.best = cur;
-      if (st.count > n_iter_no_change) { st.stopped = 1; s_stop = 1; }
+      if (st.count > n_iter_no_change) {
+        st.stopped = 1;
+        for (int c = 0; c < TRAIN_CTAS; ++c) cluster.map_shared_rank(misc, c)[34] = 1.0;
+      }
     }
-    __syncthreads();
+    cluster.sync();
   }
-  for (int i = tid; i < 3 * P; i += blockDim.x) theta_g[i] = th[i];
-  if (tid == 0) *state_g = st;
+  for (int i = L.slice0 + tid; i < L.slice1; i += blockDim.x) {
+    theta_g[i] = th[i];
+    theta_g[P + i] = mo[i - L.slice0];
+    theta_g[2 * P + i] = ve[i - L.slice0];
+  }
+  if (rank == 0 && tid == 0) { st.t = t; *state_g = st; }
+  cluster.sync();                          // no CTA leaves while its shared memory may still be addressed
 }
 
 // forward pass of explicit 0/1 rows with the current parameters (MLPRegressor.predict): one warp per row
@@ -214,11 +364,7 @@ __global__ void predict_kernel(int K, int H, long long n, const uint8_t *__restr
   if (lane == 0) out[r] = term + theta[P1 + H];
 }
 
-size_t train_smem_bytes(int K, int H, int batch) {
-  const size_t P = (size_t)(K + 1) * H + H + 1;
-  const int KW = (K + 31) / 32;
-  return (3 * P + (size_t)batch * H + batch + H + 1 + 34) * 8 + (size_t)batch * KW * 4 + 16;
-}
+size_t train_smem_bytes(int K, int H, int batch) { return train_layout(K, H, batch, 0).bytes; }
 
 }  // namespace
 
@@ -231,8 +377,8 @@ int so_trainer_create(int device, int64_t n_rows, int K, int H, const uint8_t *X
   SO_REQUIRE(X && y && W1 && b1 && w2 && hp, "NULL argument");
   SO_REQUIRE(n_rows >= 1 && n_rows < (1LL << 31), "n_rows=%lld out of range", (long long)n_rows);
   SO_REQUIRE(K >= 1 && H >= 1 && H <= 31, "K=%d, H=%d: need K >= 1 and 1 <= H <= 31", K, H);
-  SO_REQUIRE(hp->batch_size >= 1 && hp->batch_size <= TRAIN_THREADS, "batch_size=%d out of range [1,%d]", hp->batch_size,
-             TRAIN_THREADS);
+  SO_REQUIRE(hp->batch_size >= 1 && hp->batch_size <= TRAIN_MAX_BATCH, "batch_size=%d out of range [1,%d]", hp->batch_size,
+             TRAIN_MAX_BATCH);
   SO_REQUIRE(hp->lr > 0 && hp->alpha >= 0 && hp->beta1 >= 0 && hp->beta1 < 1 && hp->beta2 >= 0 && hp->beta2 < 1 && hp->eps > 0,
              "invalid Adam hyper-parameters");
   int n_dev = 0;
@@ -344,7 +490,7 @@ int so_trainer_run(so_trainer *t, int n_epochs, const int32_t *orders, double *l
     if (e == cudaSuccess) e = cudaMemsetAsync(loss_dev, 0, (size_t)n_epochs * 8, t->stream);
     if (e == cudaSuccess) e = cudaEventRecord(t->ev0, t->stream);
     if (e == cudaSuccess) {
-      train_kernel<<<1, TRAIN_THREADS, t->smem, t->stream>>>(t->K, t->KW, t->H, t->batch, t->n_rows, t->xbits_dev, t->y_dev,
+      train_kernel<<<TRAIN_CTAS, TRAIN_THREADS, t->smem, t->stream>>>(t->K, t->KW, t->H, t->batch, t->n_rows, t->xbits_dev, t->y_dev,
                                                              t->theta_dev, t->state_dev, n_epochs, ord_dev, loss_dev, t->lr,
                                                              t->alpha, t->beta1, t->beta2, t->eps, t->tol, t->n_iter_no_change);
       e = cudaGetLastError();
