@@ -135,7 +135,8 @@ typedef struct so_anneal_args {
   int exact_guard;           /* 1: re-decide near-ties with fp64 weights           */
   double guard_tol;          /* |delta - T ln u| below which the guard fires       */
   int variant;               /* 0 = auto; tests: 1 = row-per-lane global-memory kernel, 2 = generic flat kernel,
-                                3 = auto without the shared-memory-resident kernel of small lattices */
+                                3 = auto without the shared-memory-resident kernels of small lattices,
+                                4 = resident warp-per-chain kernel, 5 = resident CTA-per-chain kernel */
 } so_anneal_args;
 
 typedef struct so_anneal_stats {

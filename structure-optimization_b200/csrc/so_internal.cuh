@@ -103,7 +103,8 @@ struct SaParams {
   uint8_t *accept_out;
   int exact_guard;
   double guard_tol;
-  int variant;                          // 0 auto, 1 row-per-lane (gated) kernel, 2 generic flat kernel, 3 auto without the resident kernel
+  int variant;                          // 0 auto, 1 row-per-lane (gated) kernel, 2 generic flat kernel, 3 auto without the resident kernel,
+                                        // 4 resident warp-per-chain kernel even for few chains, 5 CTA-per-chain kernel
   unsigned long long *counters;
   uint32_t *gate_scratch;
   SurView sv;
@@ -146,6 +147,8 @@ size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);
 bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem);
 bool so_gate_index_ok(const so_surrogate *s, int N, int W);
+bool so_team_ok(const so_surrogate *s, int N, int W, long long n_chains, int n_sm);
+int so_launch_anneal_team(const so_chains *c, const SaParams &P, cudaStream_t st);
 int so_launch_anneal_gate_index(const so_chains *c, const SaParams &P, cudaStream_t st);
 int so_launch_apply_flips(const so_chains *c, int64_t n, const int64_t *chains_dev, const int32_t *sites_dev,
                           cudaStream_t st);

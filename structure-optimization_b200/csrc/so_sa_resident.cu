@@ -418,6 +418,269 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
   }
 }
 
+
+// ---- few chains: one CTA (TEAM_WARPS warps) per chain -------------------------------------------------------------------
+// The reference anneals ONE chain per process; with a warp per chain a launch of a few chains leaves the GPU idle and
+// a step costs the latency of one warp walking all K rows.  Here a chain's step is spread over the warps of a CTA:
+// the gate pass by row groups of 32 (one group per warp at K = 144), the difference pass by the same groups (gated) or
+// by contiguous column chunks (open); every warp reduces its part exactly (REDUX limbs), the parts meet in shared
+// memory at one __syncthreads per step, and every thread takes the same decision from the same sums.  Same caches
+// (gate bits, path index) and same arithmetic as sa_resident_kernel: results are bit-identical.
+constexpr int TEAM_WARPS = 4;
+
+template <int HP4, bool GATED>
+__global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int RPP = 32 / HP4, STRIDE = RPP * HP4;
+  const SurView &sv = P.sv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d, N = P.N, K = sv.K, KW = (K + 31) >> 5, W = P.W;
+  const int n_tree = GATED ? sv.n_tree : 0;
+  // shared layout: [W1q][tree][offsets][w2q][hq: N*HP4 int4][parts: 2 x TEAM_WARPS x 3 int64][chain id][bits W][act W]
+  // [S: N*KW][lists: KW*32 u32][positions: K u16][counts: KW int]
+  int4 *s_W = (int4 *)s_raw;
+  int4 *s_tree = s_W + (size_t)K * HP4;
+  int32_t *s_off = (int32_t *)(s_tree + n_tree);
+  int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
+  int4 *hq = s_w2 + HP4;
+  long long *s_part = (long long *)(hq + (size_t)N * HP4);
+  long long *s_chain = s_part + 2 * TEAM_WARPS * 3;
+  uint32_t *s_bits = (uint32_t *)(s_chain + 1);
+  uint32_t *s_act = s_bits + W;
+  uint32_t *s_S = s_act + W;
+  uint32_t *s_list = s_S + (GATED ? N * KW : 0);
+  int *s_cnt = (int *)(s_list + (GATED ? KW * 32 : 0));
+  unsigned short *s_pos = (unsigned short *)(s_cnt + KW);
+  for (int q = threadIdx.x; q < K * HP4; q += blockDim.x) s_W[q] = ((const int4 *)sv.W1q)[q];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
+  if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)sv.w2q)[threadIdx.x];
+  if (GATED)
+    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree[i] = sv.t_packed[i];
+  const int part = lane % HP4, rsub = lane / HP4;
+  const bool worker = lane < STRIDE;
+  const int4 w2 = worker ? __ldg((const int4 *)sv.w2q + part) : make_int4(0, 0, 0, 0);
+  const float tol_f = (float)P.guard_tol;
+  const bool guard_on = P.exact_guard != 0;
+  const int chunk = (K + TEAM_WARPS - 1) / TEAM_WARPS;      // open: columns [warp * chunk, (warp + 1) * chunk)
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_chain = (long long)atomicAdd(P.counters, 1ULL);
+    __syncthreads();
+    const long long c = *s_chain;
+    if (c >= P.n_chains) break;
+    uint32_t *bits_g = P.bits + c * W;
+    int4 *hq_g = (int4 *)P.hq + c * (long long)N * HP4;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = bits_g[w];
+    for (int q = threadIdx.x; q < N * HP4; q += blockDim.x) hq[q] = hq_g[q];
+    if (GATED)
+      for (int i = threadIdx.x; i < N * KW; i += blockDim.x) s_S[i] = 0u;
+    long long hi = P.hi[c], lo = P.lo[c];      // tracked identically by every thread
+    int nact = P.nact[c];
+    const double tsc = P.tscale[c];
+    const float tsc_f = (float)tsc;
+    unsigned n_acc = 0, n_guard = 0;
+    __syncthreads();
+    if (GATED) {
+      for (int r0 = 32 * warp; r0 < N; r0 += 32 * TEAM_WARPS) {
+        const int r = r0 + lane;
+        int g = 0;
+        if (r < N) {
+          const int r2 = r / d;
+          g = walk_mark<true>(s_tree, s_bits, s_S, KW, d, r - r2 * d, r2);
+        }
+        __syncwarp();
+        const unsigned m = __ballot_sync(SO_FULL, g);
+        if (lane == 0) s_act[r0 >> 5] = m;
+      }
+      __syncthreads();
+    }
+    DrawR batch;
+    batch.f = 0; batch.u = 0.f; batch.tf = 0.f;
+
+    for (long long s = 0; s < P.n_steps; ++s) {
+      if ((s & 31) == 0)
+        batch = draw_batch_res(P.temps, P.proposals, P.uniforms, P.n_steps, P.step0, P.chain_id0 + c, c, P.seed, N, d,
+                               s >> 5, lane);
+      const int fp = __shfl_sync(SO_FULL, batch.f, (int)(s & 31));
+      const float u = __shfl_sync(SO_FULL, batch.u, (int)(s & 31));
+      const float Tf = tsc_f * __shfl_sync(SO_FULL, batch.tf, (int)(s & 31));
+      const int f1 = fp & 0xffff, f2 = fp >> 16;
+      const int f = f2 * d + f1;
+      const int sgn = ((s_bits[f >> 5] >> (f & 31)) & 1) ? -1 : 1;
+      long long dhi = 0;
+      int dlo = 0, dn = 0;
+      unsigned mywalk = 0, mychg = 0;      // bit j: this lane's row of group j (groups j = warp, warp + TEAM_WARPS, ...)
+      int ax = 0, ay = 0, az = 0, aw = 0;
+      if (GATED) {
+        unsigned g0m = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int j = warp; j < KW; j += TEAM_WARPS) {
+          const int k = 32 * j + lane;
+          const bool valid = k < K;
+          const int off = s_off[valid ? k : 0];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const unsigned g0 = valid ? (s_act[row >> 5] >> (row & 31)) & 1u : 0u;
+          g0m |= g0 << j;
+          mywalk |= ((s_S[f * KW + j] >> lane) & 1u) << j;
+          const unsigned m = __ballot_sync(SO_FULL, g0);
+          if (g0) {
+            const int pos = __popc(m & lt);
+            s_list[32 * j + pos] = (unsigned)(k << 16) | 0x8000u | (unsigned)row;
+            s_pos[k] = (unsigned short)pos;
+          }
+          if (lane == 0) s_cnt[j] = __popc(m);
+        }
+        unsigned g1m = g0m;
+        for (unsigned todo = mywalk; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1;
+          const int off = s_off[32 * j + lane];
+          const unsigned g1 = walk1(s_tree, s_bits, d, f, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+          g1m = (g1m & ~(1u << j)) | (g1 << j);
+        }
+        __syncwarp();
+        mychg = g0m ^ g1m;
+        for (unsigned todo = mychg; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1, k = 32 * j + lane;
+          const int off = s_off[k];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const int on = (g1m >> j) & 1;
+          if (!on) s_list[32 * j + s_pos[k]] &= ~0x8000u;
+          const long long A = row_sum_res<HP4>(hq + row * HP4, s_W + k * HP4, s_w2, on ? sgn : 0);
+          const int sg = on ? 1 : -1;
+          dhi += sg * (A >> SO_SPLIT_BITS);
+          dlo += sg * (int)(A & SO_SPLIT_MASK);
+          dn += sg;
+        }
+        __syncwarp();
+        if (worker) {
+          for (int j = warp; j < KW; j += TEAM_WARPS) {
+            const int cnt = s_cnt[j];
+            for (int i = rsub; i < cnt; i += RPP) {
+              const unsigned e = s_list[32 * j + i];
+              const int sg = sgn & -(int)((e >> 15) & 1u);
+              const int4 h = hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
+              ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
+              ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
+              az += max(h.z + sg * w.z, 0) - max(h.z, 0);
+              aw += max(h.w + sg * w.w, 0) - max(h.w, 0);
+            }
+          }
+        }
+      } else if (worker) {
+        const int k_hi = min(K, (warp + 1) * chunk);
+#pragma unroll 4
+        for (int k = warp * chunk + rsub; k < k_hi; k += RPP) {
+          const int off = s_off[k];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const int4 h = hq[row * HP4 + part], w = s_W[k * HP4 + part];
+          ax += max(h.x + sgn * w.x, 0) - max(h.x, 0);
+          ay += max(h.y + sgn * w.y, 0) - max(h.y, 0);
+          az += max(h.z + sgn * w.z, 0) - max(h.z, 0);
+          aw += max(h.w + sgn * w.w, 0) - max(h.w, 0);
+        }
+      }
+      long long acc = (long long)w2.x * ax + (long long)w2.y * ay + (long long)w2.z * az + (long long)w2.w * aw;
+      {
+        int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
+        l0 = __reduce_add_sync(SO_FULL, l0);
+        l1 = __reduce_add_sync(SO_FULL, l1);
+        l2 = __reduce_add_sync(SO_FULL, l2);
+        acc = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
+      }
+      long long dlo_w = acc & SO_SPLIT_MASK;
+      if (GATED && __any_sync(SO_FULL, mychg != 0)) {
+        int l0 = (int)(dhi & 0x1fffff), l1 = (int)((dhi >> 21) & 0x1fffff), l2 = (int)(dhi >> 42);
+        l0 = __reduce_add_sync(SO_FULL, l0);
+        l1 = __reduce_add_sync(SO_FULL, l1);
+        l2 = __reduce_add_sync(SO_FULL, l2);
+        dhi = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
+        dn = __reduce_add_sync(SO_FULL, dn);
+        dlo_w += (long long)__reduce_add_sync(SO_FULL, dlo);
+      }
+      dhi += acc >> SO_SPLIT_BITS;
+      // the warps' parts meet here (double-buffered by step parity: one barrier per step is enough)
+      long long *mine = s_part + ((s & 1) * TEAM_WARPS + warp) * 3;
+      if (lane == 0) { mine[0] = dhi; mine[1] = dlo_w; mine[2] = dn; }
+      __syncthreads();
+      dhi = 0; dlo_w = 0; dn = 0;
+#pragma unroll
+      for (int w = 0; w < TEAM_WARPS; ++w) {
+        const long long *o = s_part + ((s & 1) * TEAM_WARPS + w) * 3;
+        dhi += o[0]; dlo_w += o[1]; dn += (int)o[2];
+      }
+      const double delta = so_real(sv.c, sv.b2, sv.y_scale, sv.y_mean, dhi, dlo_w, dn);
+      bool accept;
+      {
+        const float pf = __expf(__fdividef((float)delta, Tf));
+        if (delta > 0.0 && (Tf > 0.f || !guard_on)) {
+          accept = true;
+        } else if (delta <= 0.0 && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u) &&
+                   (!guard_on || tol_f < 2.5e-4f * Tf)) {
+          accept = pf > u;
+        } else {
+          int r = decide_res(delta, tsc, P.temps, s, u, P.exact_guard, P.guard_tol);
+          if (r & 2) {
+            r = exact_decision_res(sv, s_bits, d, f, lane, tsc, P.temps, s, u);     // every warp, same result
+            ++n_guard;
+          }
+          accept = r & 1;
+        }
+      }
+      if (accept) {                                  // uniform over the CTA
+        if (GATED) {
+          for (unsigned todo = mywalk; todo; todo &= todo - 1) {
+            const int off = s_off[32 * (__ffs(todo) - 1) + lane];
+            walk_mark<false>(s_tree, s_bits, s_S, KW, d, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+          }
+          for (unsigned todo = mychg; todo; todo &= todo - 1) {
+            const int off = s_off[32 * (__ffs(todo) - 1) + lane];
+            const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+            atomicXor(s_act + (row >> 5), 1u << (row & 31));
+          }
+        }
+        if (worker) {
+          const int k_hi = min(K, (warp + 1) * chunk);
+          for (int k = warp * chunk + rsub; k < k_hi; k += RPP) {
+            const int off = s_off[k];
+            int4 *hp = hq + (wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d)) * HP4 + part;
+            int4 h = *hp;
+            const int4 w = s_W[k * HP4 + part];
+            h.x += sgn * w.x; h.y += sgn * w.y; h.z += sgn * w.z; h.w += sgn * w.w;
+            *hp = h;
+          }
+        }
+        __syncthreads();                             // old paths dropped everywhere before the bit flips
+        if (threadIdx.x == 0) s_bits[f >> 5] ^= (1u << (f & 31));
+        __syncthreads();
+        if (GATED) {
+          for (unsigned todo = mywalk; todo; todo &= todo - 1) {
+            const int off = s_off[32 * (__ffs(todo) - 1) + lane];
+            walk_mark<true>(s_tree, s_bits, s_S, KW, d, wrap(f1 - (int)(short)(off & 0xffff), d), wrap(f2 - (off >> 16), d));
+          }
+          __syncthreads();
+        }
+        lo += dlo_w;
+        hi += dhi + (lo >> SO_SPLIT_BITS);
+        lo &= SO_SPLIT_MASK;
+        nact += dn;
+        ++n_acc;
+      }
+      if (P.accept_out && threadIdx.x == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) bits_g[w] = s_bits[w];
+    for (int q = threadIdx.x; q < N * HP4; q += blockDim.x) hq_g[q] = hq[q];
+    if (threadIdx.x == 0) {
+      P.hi[c] = hi;
+      P.lo[c] = lo;
+      P.nact[c] = nact;
+      if (n_acc) atomicAdd(P.counters + 1, (unsigned long long)n_acc);
+      if (n_guard) atomicAdd(P.counters + 2, (unsigned long long)n_guard);
+    }
+  }
+}
+
 }  // namespace
 
 static size_t shared_tables_bytes(const so_surrogate *s) {
@@ -450,6 +713,40 @@ bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_
   if (warps_out) *warps_out = best_w;
   if (smem_out) *smem_out = best_smem;
   return true;
+}
+
+// few chains on a small lattice: one CTA per chain (sa_team_kernel)
+static size_t team_smem_bytes(const so_surrogate *s, int N, int W) {
+  const int KW = (s->K + 31) / 32;
+  size_t b = shared_tables_bytes(s) + (size_t)N * s->HP4 * 16 + (size_t)(2 * W) * 4;
+  if (s->gated) b += (size_t)(N * KW + KW * 32) * 4 + a16((size_t)s->K * 2);
+  return b + a16((size_t)KW * 4) + 2 * TEAM_WARPS * 3 * 8 + 8 + 64;
+}
+bool so_team_ok(const so_surrogate *s, int N, int W, long long n_chains, int n_sm) {
+  return shape_ok(s, N) && n_chains <= 2LL * n_sm && team_smem_bytes(s, N, W) <= 100 * 1024;
+}
+
+int so_launch_anneal_team(const so_chains *c, const SaParams &P, cudaStream_t st) {
+  const so_surrogate *s = c->sur;
+  const size_t smem = team_smem_bytes(s, P.N, P.W);
+  const int blocks = (int)P.n_chains, warps = TEAM_WARPS;
+#define SO_TEAM_LAUNCH(V, G)                                                                               \
+  {                                                                                                        \
+    auto kern = sa_team_kernel<V, G>;                                                                      \
+    SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
+  }
+#define SO_RES_CASE(V) \
+  case V:              \
+    if (s->gated) SO_TEAM_LAUNCH(V, true) else SO_TEAM_LAUNCH(V, false) break;
+  switch (s->HP4) {
+    SO_RES_CASE(1) SO_RES_CASE(2) SO_RES_CASE(3) SO_RES_CASE(4) SO_RES_CASE(5) SO_RES_CASE(6) SO_RES_CASE(7) SO_RES_CASE(8)
+    default: so_set_error("hidden width not supported"); return SO_EINVAL;
+  }
+#undef SO_RES_CASE
+#undef SO_TEAM_LAUNCH
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
 }
 
 // gated surrogate on a lattice too large for shared memory: can the cached-gate kernel (global state) run it?

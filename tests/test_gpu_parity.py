@@ -244,8 +244,9 @@ def test_sa_flat_local_descriptor(eng):
     _run_sa(eng, 16, p, n_chains=40, steps=2000, seed=22)
 
 
-# variant 0 picks the shared-memory-resident kernel on these small lattices, variant 3 the pipelined window kernel
-@pytest.mark.parametrize("variant", [0, 3])
+# variant 0 picks a shared-memory-resident kernel on these small lattices (CTA per chain for few chains, warp per chain
+# for many), variant 4 the warp-per-chain one, variant 3 the pipelined window kernel
+@pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("T0", [0.05, 2.0])
 def test_sa_flat_local_small_lattice_wrap(eng, T0, variant):
     """7x7 window on a 7x7 lattice: every wrap path, and (hot run: most flips accepted) every prefetched window is
@@ -256,7 +257,7 @@ def test_sa_flat_local_small_lattice_wrap(eng, T0, variant):
         assert r["acc"].mean() > 0.5
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 @pytest.mark.parametrize("d", [8, 12, 20])
 def test_sa_window_hot_chains(eng, d, variant):
     """High acceptance on small lattices: overlapping windows of consecutive flips are the common case."""
@@ -265,7 +266,7 @@ def test_sa_window_hot_chains(eng, d, variant):
     assert r["acc"].mean() > 0.1
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 def test_sa_window_many_chains(eng, variant):
     """More chains than resident warps: dynamic chain hand-out + stage/mbarrier reuse across chains."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=41)
@@ -311,25 +312,41 @@ def test_sa_gated_local_large_lattice(eng, d, T0, variant):
         assert r["acc"].mean() > 0.1
 
 
+@pytest.mark.parametrize("variant", [4, 5])
 @pytest.mark.parametrize("d", [8, 12])
-def test_sa_gated_hot_resident(eng, d):
-    """Resident gated kernel at high acceptance (index upkeep every few steps), local window with wraps."""
+def test_sa_gated_hot_resident(eng, d, variant):
+    """Resident gated kernels (4: warp per chain, 5: CTA per chain) at high acceptance (index upkeep every few steps),
+    local window with wraps."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=80 + d)
     p.tree = _random_tree(49, 8, seed=100 + d)
-    r = _run_sa(eng, d, p, n_chains=24, steps=1500, seed=90 + d, T0=2.0, cooling="const")
+    r = _run_sa(eng, d, p, n_chains=24, steps=1500, seed=90 + d, T0=2.0, cooling="const", variant=variant)
     assert r["acc"].mean() > 0.1
 
 
+@pytest.mark.parametrize("variant", [4, 5])
+@pytest.mark.parametrize("gated", [False, True])
+def test_sa_resident_full_descriptor_variants(eng, gated, variant):
+    """Full 144-column descriptor (the reference's shape), golden MLP (+ tree), both resident kernels, Philox draws and
+    injected draws, odd lattice for ragged row groups."""
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=gated), n_chains=10, steps=1200, seed=31, variant=variant, T0=0.2)
+    _run_sa(eng, 12, Hp.golden_surrogate(gated=gated), n_chains=5, steps=700, seed=32, variant=variant, use_philox=True)
+    p = S.SurrogateParams.random_init(L.local_offsets(2), H=7, seed=33)
+    if gated:
+        p.tree = _random_tree(25, 5, seed=34)
+    _run_sa(eng, 9, p, n_chains=7, steps=900, seed=35, variant=variant, T0=1.0, cooling="const")
+
+
 def test_sa_kernel_variants_agree(eng):
-    """resident == window (pipelined) == generic flat == row-per-lane kernels, bit for bit."""
+    """CTA-per-chain (auto choice for 12 chains) == resident warp-per-chain == window (pipelined) == generic flat ==
+    row-per-lane kernels, bit for bit."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
     a = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=0, T0=0.3)
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4, 5):
         b = _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=25, variant=variant, T0=0.3)
         assert (a["acc"] == b["acc"]).all() and (a["x1"] == b["x1"]).all() and (a["of"] == b["of"]).all()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_sa_philox_draws(eng, variant):
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=6)
     _run_sa(eng, 12, p, n_chains=12, steps=1000, seed=26, use_philox=True, variant=variant)
