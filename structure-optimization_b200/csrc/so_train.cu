@@ -5,8 +5,8 @@
 // Training is a strictly sequential chain of tiny batches (200 rows x K x H: ~0.6 M fp64 additions per step after
 // exploiting the 0/1 inputs, up to ~1e6 steps), so it runs as ONE persistent thread-block cluster of 8 CTAs with the
 // whole optimiser state in (distributed) shared memory: every CTA keeps a replica of the parameters and works on an
-// eighth of each batch's rows (rows as bit-vectors: the first layer is a sum of weight rows over set bits, its gradient
-// a sum of delta rows over the set bits of the ballot-transposed batch); the gradients are reduce-scattered through
+// eighth of each batch's rows (rows as bit-vectors, expanded to 0/1 operands of fp64 tensor-core tiles for the two small
+// GEMMs of a step); the gradients are reduce-scattered through
 // DSMEM, each CTA applies Adam to the parameter slice whose moments it owns and stores the result into all replicas.
 // Nothing but the batch rows (K/8 B each) and the targets is read from HBM per step.  The order of the samples in every
 // epoch is supplied by the caller, so a run can replay scikit-learn's own shuffles (parity tests) or any other stream.
@@ -57,33 +57,19 @@ constexpr int TRAIN_THREADS = 1024;
 constexpr int TRAIN_CTAS = 8;            // one thread-block cluster
 constexpr int TRAIN_MAX_BATCH = 1024;    // <= 128 rows per CTA (four row words)
 
-// block-wide sums of two values at once; results in scratch[32] and scratch[36]
-__device__ __forceinline__ void block_sum2(double v, double w, double *scratch) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v += __shfl_xor_sync(SO_FULL, v, o);
-    w += __shfl_xor_sync(SO_FULL, w, o);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) { scratch[warp] = v; scratch[40 + warp] = w; }
-  __syncthreads();
-  if (warp == 0) {
-    v = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.0;
-    w = lane < (int)(blockDim.x >> 5) ? scratch[40 + lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v += __shfl_xor_sync(SO_FULL, v, o);
-      w += __shfl_xor_sync(SO_FULL, w, o);
-    }
-    if (lane == 0) { scratch[32] = v; scratch[36] = w; }
-  }
-  __syncthreads();
+// D (8x8) += A (8x4, row-major) * B (4x8, column-major) on the fp64 tensor cores.  Fragments (lane l): a = A[l/4][l%4],
+// b = B[l%4][l/4], c0/c1 = C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double bit_to_double(unsigned bit) { return __hiloint2double((int)(bit * 0x3ff00000u), 0); }
 
 struct TrainLayout {       // shared memory of one CTA, in doubles unless noted
   int P1, P, slice0, slice1, rows_max, RW;
-  size_t th, gp, mo, ve, act, d2, misc, xb, xt, bytes;
+  int KS, Hpad;
+  size_t th, gp, mo, ve, act, del, d2, sqr, misc, fpart, xb, bytes;
 };
 __host__ __device__ inline TrainLayout train_layout(int K, int H, int batch, int rank) {
   TrainLayout L;
@@ -101,11 +87,19 @@ __host__ __device__ inline TrainLayout train_layout(int K, int H, int batch, int
   o += 2;                                    // [P + 1] = sum of squares of the coefficients in its slice
   L.mo = o; o += slice_max;                  // Adam moments of this CTA's parameter slice
   L.ve = o; o += slice_max;
-  L.act = o; o += (size_t)L.rows_max * H;    // activations, then delta1, of this CTA's rows
-  L.d2 = o; o += L.rows_max;
+  L.act = o; o += (size_t)L.rows_max * H;    // activations of this CTA's rows
+  L.del = o; o += (size_t)L.rows_max * H;    // delta1 of this CTA's rows
+  L.d2 = o; o += L.rows_max;                 // targets, then residuals
+  L.sqr = o; o += L.rows_max;                // squared residuals
   L.misc = o; o += 72;                       // block reduction scratch [0..32], [36], [40..71]; lr_t [33], [35]; stop flag [34]
+  // forward tiles: MT x NT output tiles of 8 x 8, the K dimension cut into KS slices so that all 32 warps have a tile
+  L.Hpad = (H + 7) & ~7;
+  {
+    const int tiles = ((L.rows_max + 7) / 8) * (L.Hpad / 8);
+    L.KS = tiles >= 32 ? 1 : (32 / tiles > 4 ? 4 : 32 / tiles);
+  }
+  L.fpart = o; o += (size_t)L.KS * (((L.rows_max + 7) / 8) * 8) * L.Hpad;   // [KS][rows padded to 8][Hpad] partial pre-activations
   L.xb = o * 8; o += ((size_t)L.rows_max * KW + 1) / 2;      // u32 [rows][KW]
-  L.xt = o * 8; o += ((size_t)(K + 1) * L.RW + 1) / 2;       // u32 [K + 1][RW]: column k as a bit mask over the rows
   L.bytes = o * 8 + 16;
   return L;
 }
@@ -124,11 +118,12 @@ __global__ void __cluster_dims__(TRAIN_CTAS, 1, 1) __launch_bounds__(TRAIN_THREA
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const TrainLayout L = train_layout(K, H, batch, rank);
-  const int P1 = L.P1, P = L.P, RW = L.RW;
+  const int P1 = L.P1, P = L.P;
   double *base = (double *)s_raw;
   double *th = base + L.th, *gp = base + L.gp, *mo = base + L.mo, *ve = base + L.ve, *act = base + L.act;
-  double *d2 = base + L.d2, *misc = base + L.misc;
-  uint32_t *xb = (uint32_t *)(s_raw + L.xb), *xt = (uint32_t *)(s_raw + L.xt);
+  double *d2 = base + L.d2, *misc = base + L.misc, *del = base + L.del, *sqr = base + L.sqr;
+  uint32_t *xb = (uint32_t *)(s_raw + L.xb);
+  double *fpart = base + L.fpart;
   __shared__ TrainState st;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double *gp_of[TRAIN_CTAS];
@@ -203,63 +198,53 @@ __global__ void __cluster_dims__(TRAIN_CTAS, 1, 1) __launch_bounds__(TRAIN_THREA
         if (s0 + batch < n_rows) fetch(e, s0 + batch);
         else if (e + 1 < n_epochs) fetch(e + 1, 0);
       }
-      // ---- columns as bit masks over the rows (ballot transpose); column K = all rows (bias) ----
-      for (int i = warp; i < (K + 1) * RW; i += (int)(blockDim.x >> 5)) {
-        const int k = i / RW, q = i - k * RW, r = 32 * q + lane;
-        const unsigned bit = r < nr ? (k < K ? (xb[r * KW + (k >> 5)] >> (k & 31)) & 1u : 1u) : 0u;
-        const unsigned m = __ballot_sync(SO_FULL, bit);
-        if (lane == 0) xt[i] = m;
-      }
-      // ---- forward, first layer: a[r][j] = relu(b1[j] + sum over set bits k of W1[k][j]) ----
-      // (two adjacent lanes per (row, unit): each sums half of the row's words, so the dependent chains are half as long)
+      // ---- forward, first layer on the fp64 tensor cores: X (rows x K, 0/1 from the bit-vectors) * W1 (K x H) ----
       {
-        const int KWh = (KW + 1) >> 1, n_slots = 2 * nr * H;
-        for (int q0 = 0; q0 < n_slots; q0 += blockDim.x) {
-          const int q = q0 + tid, p = q >> 1;
-          double h0 = 0.0, h1 = 0.0;
-          int r = 0, j = 0;
-          if (q < n_slots) {
-            r = p / H;
-            j = p - r * H;
-            const int w_lo = (q & 1) ? KWh : 0, w_hi = (q & 1) ? KW : KWh;
-            for (int w = w_lo; w < w_hi; ++w) {
-              // set bits only: half the shared-memory traffic of a predicated sweep over all positions, which measured
-              // slower (the loop is bound by LDS.64 bandwidth and issue together)
-              uint32_t bits = xb[r * KW + w];
-              const double *row = th + (size_t)(32 * w) * H + j;
-              while (bits) {
-                const int k0 = __ffs(bits) - 1;
-                bits &= bits - 1;
-                h0 += row[k0 * H];
-                if (bits) {
-                  const int k1 = __ffs(bits) - 1;
-                  bits &= bits - 1;
-                  h1 += row[k1 * H];
-                }
-              }
-            }
+        const int MT = (nr + 7) >> 3, NT = L.Hpad >> 3, KS = L.KS, rows_pad = ((L.rows_max + 7) >> 3) << 3;
+        const int ksteps = (K + 3) >> 2, per = (ksteps + KS - 1) / KS;
+        const int ar = lane >> 2, ak = lane & 3;                  // fragment coordinates of this lane
+        for (int t = warp; t < MT * NT * KS; t += (int)(blockDim.x >> 5)) {
+          const int ks = t / (MT * NT), mt = (t / NT) % MT, nt = t % NT;
+          const int row = 8 * mt + ar, col = 8 * nt + ar;
+          const uint32_t *xrow = xb + (row < nr ? row : 0) * KW;
+          double c0 = 0.0, c1 = 0.0;
+          const int kk_hi = min(ksteps, (ks + 1) * per);
+          for (int kk = ks * per; kk < kk_hi; ++kk) {
+            const int k = 4 * kk + ak;
+            const unsigned bit = (row < nr && k < K) ? (xrow[k >> 5] >> (k & 31)) & 1u : 0u;
+            const double b = (k < K && col < H) ? th[k * H + col] : 0.0;
+            dmma884(c0, c1, bit_to_double(bit), b);
           }
-          h0 += h1;
-          const double other = __shfl_xor_sync(SO_FULL, h0, 1);
-          if (q < n_slots && !(q & 1)) act[p] = fmax(th[K * H + j] + h0 + other, 0.0);
+          double *o = fpart + ((size_t)ks * rows_pad + 8 * mt + ar) * L.Hpad + 8 * nt + 2 * ak;
+          o[0] = c0;
+          o[1] = c1;
         }
       }
       __syncthreads();
-      // ---- output, residual, loss terms ----
-      double part = 0.0;
-      if (tid < nr) {
-        double pred = th[P1 + H];
-        for (int j = 0; j < H; ++j) pred += act[tid * H + j] * th[P1 + j];
-        const double dd = pred - d2[tid];
-        d2[tid] = dd;
-        part = dd * dd;
+      // ---- one warp per row: bias + relu, output, residual, delta1 (lane j = hidden unit j; no barrier in between) ----
+      {
+        const int rows_pad = ((L.rows_max + 7) >> 3) << 3;
+        for (int r = warp; r < nr; r += (int)(blockDim.x >> 5)) {
+          double a = 0.0, w2j = 0.0;
+          if (lane < H) {
+            double h = th[K * H + lane];
+            for (int ks = 0; ks < L.KS; ++ks) h += fpart[((size_t)ks * rows_pad + r) * L.Hpad + lane];   // fixed order
+            a = fmax(h, 0.0);
+            w2j = th[P1 + lane];
+            act[r * H + lane] = a;
+          }
+          double pred = a * w2j;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pred += __shfl_xor_sync(SO_FULL, pred, o);
+          const double dd = pred + th[P1 + H] - d2[r];
+          if (lane < H) del[r * H + lane] = a > 0.0 ? dd * w2j : 0.0;
+          __syncwarp();
+          if (lane == 0) { d2[r] = dd; sqr[r] = dd * dd; }
+        }
       }
-      double part2 = 0.0;                  // squares of the coefficients (not intercepts) of this CTA's slice
-      for (int p = L.slice0 + tid; p < L.slice1; p += blockDim.x)
-        if (p < K * H || (p >= P1 && p < P1 + H)) part2 += th[p] * th[p];
-      block_sum2(part, part2, misc);
-      if (tid == 0) { gp[P] = misc[32]; gp[P + 1] = misc[36]; }
-      // ---- partial gradients of the output layer (warp j: column j of a^T delta2; warp H: sum of delta2) ----
+      __syncthreads();
+      // ---- output-layer partial gradients (warp j < H: column j of a^T delta2; warp H: sum of delta2) and the loss terms
+      //      (last warp: squared residuals of this CTA's rows, squared coefficients of its slice) ----
       if (warp <= H) {
         double g = 0.0;
         for (int r = lane; r < nr; r += 32) g += (warp < H ? act[r * H + warp] : 1.0) * d2[r];
@@ -267,32 +252,38 @@ __global__ void __cluster_dims__(TRAIN_CTAS, 1, 1) __launch_bounds__(TRAIN_THREA
         for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(SO_FULL, g, o);
         if (lane == 0) gp[P1 + warp] = g;
       }
-      __syncthreads();
-      // ---- delta1 in place of the activations ----
-      for (int p = tid; p < nr * H; p += blockDim.x) {
-        const int r = p / H, j = p - r * H;
-        act[p] = act[p] > 0.0 ? d2[r] * th[P1 + j] : 0.0;
+      if (warp == (int)(blockDim.x >> 5) - 1) {
+        double part = 0.0, part2 = 0.0;
+        for (int r = lane; r < nr; r += 32) part += sqr[r];
+        for (int p = L.slice0 + lane; p < L.slice1; p += 32)
+          if (p < K * H || (p >= P1 && p < P1 + H)) part2 += th[p] * th[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          part += __shfl_xor_sync(SO_FULL, part, o);
+          part2 += __shfl_xor_sync(SO_FULL, part2, o);
+        }
+        if (lane == 0) { gp[P] = part; gp[P + 1] = part2; }
       }
-      __syncthreads();
-      // ---- partial first-layer gradients: sum of delta1 over the rows that have column k set ----
-      for (int p = tid; p < P1; p += blockDim.x) {
-        const int k = p / H, j = p - k * H;
-        double g0 = 0.0, g1 = 0.0;
-        for (int q = 0; q < RW; ++q) {
-          uint32_t bits = xt[k * RW + q];
-          const double *col = act + (size_t)(32 * q) * H + j;
-          while (bits) {
-            const int r0 = __ffs(bits) - 1;
-            bits &= bits - 1;
-            g0 += col[r0 * H];
-            if (bits) {
-              const int r1 = __ffs(bits) - 1;
-              bits &= bits - 1;
-              g1 += col[r1 * H];
-            }
+      // ---- partial first-layer gradients on the fp64 tensor cores: X^T ((K+1) x rows; row K = ones: the bias) * delta1 ----
+      {
+        const int MT = (K + 1 + 7) >> 3, NT = L.Hpad >> 3, rsteps = (nr + 3) >> 2;
+        const int ar = lane >> 2, ak = lane & 3;
+        for (int t = warp; t < MT * NT; t += (int)(blockDim.x >> 5)) {
+          const int mt = t / NT, nt = t - mt * NT;
+          const int k = 8 * mt + ar, col = 8 * nt + ar;
+          double c0 = 0.0, c1 = 0.0;
+          for (int kk = 0; kk < rsteps; ++kk) {
+            const int r = 4 * kk + ak;
+            const unsigned bit = r < nr ? (k < K ? (xb[r * KW + (k >> 5)] >> (k & 31)) & 1u : (k == K ? 1u : 0u)) : 0u;
+            const double b = (r < nr && col < H) ? del[r * H + col] : 0.0;
+            dmma884(c0, c1, bit_to_double(bit), b);
+          }
+          const int oc = 8 * nt + 2 * ak;
+          if (k <= K) {
+            if (oc < H) gp[k * H + oc] = c0;
+            if (oc + 1 < H) gp[k * H + oc + 1] = c1;
           }
         }
-        gp[p] = g0 + g1;
       }
       cluster.sync();                      // all partial gradients are in place
       // ---- reduce-scatter + Adam on this CTA's slice; new values go to every replica ----
