@@ -24,19 +24,37 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
+OBJ_DIR = os.path.join(HERE, "_obj")          # per-source objects (git-ignored); only changed sources are recompiled
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + SOURCES
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = ["-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+        flags = ["-Xptxas", "-v"] + flags
+    hdr_t = max(os.path.getmtime(os.path.join(HERE, h)) for h in HEADERS)
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        src_t = max(os.path.getmtime(os.path.join(HERE, src)), hdr_t)
+        if not force and not verbose and os.path.exists(obj) and os.path.getmtime(obj) > src_t:
+            return obj, ""
+        res = subprocess.run([nvcc, "-c"] + flags + ["-o", obj, src], cwd=HERE, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + [o for o, _ in results], cwd=HERE, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write("".join(err for _, err in results))
     return LIB
 
 

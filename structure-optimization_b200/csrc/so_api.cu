@@ -452,7 +452,7 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
   s->b2 = b2; s->y_mean = y_mean; s->y_scale = y_scale; s->gated = n_tree_nodes > 0; s->n_tree = n_tree_nodes;
   s->offs_dev = nullptr; s->W1q_dev = s->b1q_dev = s->w2q_dev = nullptr; s->W1d_dev = s->b1d_dev = s->w2d_dev = nullptr;
   s->t_feature_dev = s->t_left_dev = s->t_right_dev = nullptr; s->t_thr_dev = nullptr; s->t_active_dev = nullptr;
-  s->t_packed_dev = nullptr; s->t_used_dev = nullptr;
+  s->t_packed_dev = nullptr;
   // fixed-point grids (identical to oracle/surrogate.py quantize)
   double bound = 0.0, wmax = 0.0;
   for (int j = 0; j < H; ++j) {
@@ -531,11 +531,6 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
       packed[i] = nd;
     }
     if (rc == SO_OK) rc = upload(&s->t_packed_dev, packed.data(), (size_t)n_tree_nodes);
-    // columns whose bit can change the outcome of some node's test (both flags equal = the test ignores the bit)
-    std::vector<uint32_t> used((size_t)(K + 31) / 32, 0u);
-    for (int i = 0; i < n_tree_nodes; ++i)
-      if (feature[i] >= 0 && ((packed[i].w >> 2) & 1) != ((packed[i].w >> 3) & 1)) used[feature[i] >> 5] |= 1u << (feature[i] & 31);
-    if (rc == SO_OK) rc = upload(&s->t_used_dev, used.data(), used.size());
   }
   if (rc != SO_OK) { so_surrogate_destroy(s); return rc; }
   *out = s;
@@ -548,7 +543,7 @@ int so_surrogate_destroy(so_surrogate *s) {
   cudaFree(s->tc_image_dev); cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
   cudaFree(s->W1d_dev); cudaFree(s->b1d_dev); cudaFree(s->w2d_dev);
   cudaFree(s->t_feature_dev); cudaFree(s->t_thr_dev); cudaFree(s->t_left_dev); cudaFree(s->t_right_dev);
-  cudaFree(s->t_active_dev); cudaFree(s->t_packed_dev); cudaFree(s->t_used_dev);
+  cudaFree(s->t_active_dev); cudaFree(s->t_packed_dev);
   delete s;
   return SO_OK;
 }

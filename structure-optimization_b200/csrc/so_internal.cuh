@@ -41,7 +41,6 @@ struct so_surrogate {
   double *t_thr_dev;
   uint8_t *t_active_dev;
   int4 *t_packed_dev;                   // one record per node: {offset of the tested column (o1 | o2<<16), left, right, flags}
-  uint32_t *t_used_dev;                 // bit k: some node's test depends on descriptor column k  [ceil(K/32)]
   std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
   int win_ok, win_a1, win_b1, win_a2, win_b2;   // descriptor offsets form the full rectangle [a1,b1] x [a2,b2]
   int32_t *Wst_dev;                             // W1q rows in staged (memory) order of the window
@@ -82,7 +81,6 @@ struct SurView {
   const double *t_thr;
   const uint8_t *t_active;
   const int4 *t_packed;                 // flags: 1 leaf, 2 leaf is active, 4 go left when the bit is 0, 8 ... when it is 1; bits 8.. = column tested
-  const uint32_t *t_used;
   int n_tree;
 };
 
@@ -118,7 +116,7 @@ inline SurView make_view(const so_surrogate *s) {
   v.W1d = s->W1d_dev; v.b1d = s->b1d_dev; v.w2d = s->w2d_dev;
   v.t_feature = s->t_feature_dev; v.t_left = s->t_left_dev; v.t_right = s->t_right_dev;
   v.t_thr = s->t_thr_dev; v.t_active = s->t_active_dev; v.t_packed = s->t_packed_dev;
-  v.t_used = s->t_used_dev; v.n_tree = s->n_tree;
+  v.n_tree = s->n_tree;
   return v;
 }
 
