@@ -387,9 +387,48 @@ def run_batch_score(a):
                       "h2d_bytes_per_step": int(bits.nbytes), "d2h_bytes_per_step": int(rate.nbytes + lh.nbytes + ne.nbytes)}))
 
 
+def run_train(a):
+    """Regressor fit of train_surrogate.py:141-152 at the reference recipe's shape: 48 structures x 144
+    sites x 3 rotations = 20,736 rows of the full 144-column descriptor; a step = one epoch (104 Adam steps of 200
+    rows).  Device: so_trainer_* through DeviceMLPRegressor; beside it scikit-learn's own fit on the host cores."""
+    import warnings
+    from so_b200.train_surrogate import DeviceMLPRegressor
+    warnings.simplefilter("ignore")
+    n, K = 20736, 144
+    rng = np.random.default_rng(0)
+    X = (rng.random((n, K)) < 0.5).astype(np.float64)
+    y = np.maximum(X @ (rng.normal(size=K) / np.sqrt(K)), 0) + 0.05 * rng.normal(size=n)
+    y = (y - y.mean()) / y.std()
+    kw = dict(activation='relu', learning_rate_init=0.0001, alpha=0.1, hidden_layer_sizes=(20,), tol=1e-5, random_state=0)
+    DeviceMLPRegressor(max_iter=a.warmup, **kw).fit(X, y)
+    t0 = time.perf_counter()
+    dev = DeviceMLPRegressor(max_iter=a.steps, **kw).fit(X, y)
+    wall = time.perf_counter() - t0
+    steps = -(-n // 200) * dev.n_iter_
+    cpu = None
+    if a.cpu_flips:
+        from sklearn.neural_network import MLPRegressor
+        t0 = time.perf_counter()
+        ref = MLPRegressor(max_iter=a.steps, **kw).fit(X, y)
+        t_ref = time.perf_counter() - t0
+        cpu = {"value": steps / t_ref, "unit": "Adam steps/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": "sklearn.neural_network.MLPRegressor.fit, the call train_surrogate.py:150-152 makes, same data and "
+                         "random_state, %d epochs, %.2f s wall" % (ref.n_iter_, t_ref),
+               "loss_rel_diff": abs(ref.loss_curve_[-1] - dev.loss_curve_[-1]) / ref.loss_curve_[-1]}
+    print(json.dumps({"metric": "Adam steps/sec of the regressor fit (200-row batches, device-timed)",
+                      "value": steps / (1e-3 * dev.kernel_ms_), "unit": "Adam steps/s", "n_gpus": 1, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": dev.kernel_ms_ / dev.n_iter_, "higher_is_better": True,
+                      "data": "synthetic", "dtype": "f64",
+                      "config": {"workload": "regressor fit, %d rows x %d-column 0/1 descriptor, 144->20->1 ReLU MLP, Adam "
+                                             "lr 1e-4, alpha 0.1, batch 200; one step = one epoch" % (n, K)},
+                      "e2e": {"value": steps / wall, "unit": "Adam steps/s", "note": "DeviceMLPRegressor.fit wall time incl. "
+                              "upload, host-generated epoch orders and read-back"},
+                      "final_loss": dev.loss_curve_[-1], "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="anneal", choices=["anneal", "score"])
+    ap.add_argument("--workload", default="anneal", choices=["anneal", "score", "train"])
     ap.add_argument("--structures", type=int, default=1 << 20)
     ap.add_argument("--score-d", type=int, default=12, help="lattice edge of the batch-scoring workload")
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,6 +449,8 @@ def main():
         run_reference(a)
     elif a.workload == "score":
         run_batch_score(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_gpu(a)
 

@@ -89,22 +89,45 @@ class DeviceMLPRegressor(object):
                                        beta1=self.beta_1, beta2=self.beta_2, eps=self.epsilon, tol=self.tol,
                                        batch_size=None if self.batch_size == 'auto' else self.batch_size,
                                        n_iter_no_change=self.n_iter_no_change, device=self._device)
-        sample_idx = np.arange(n)
-        curve, status, self.kernel_ms_ = [], dict(stopped=False, n_iter=0, best_loss=np.inf), 0.0
-        while len(curve) < self.max_iter and not status['stopped']:
-            m = min(self._chunk, self.max_iter - len(curve))
+        # Epoch orders are drawn on the host exactly as sklearn.utils.shuffle draws them (cumulative permutations from the
+        # same RandomState).  The next chunk is drawn by a helper thread while the GPU runs the current one (the C call
+        # releases the GIL); when the stop rule fires inside a chunk, the generator is rewound to the state it has after
+        # the last epoch actually run, so it is left exactly where MLPRegressor.fit would leave it.
+        from concurrent.futures import ThreadPoolExecutor
+
+        def draw_chunk(sample_idx, m):
+            state = rng.get_state()
             orders = np.empty((m, n), dtype=np.int32)
-            for e in range(m):                              # sklearn.utils.shuffle(sample_idx, random_state=rng)
+            for e in range(m):
                 perm = np.arange(n)
                 rng.shuffle(perm)
                 sample_idx = sample_idx[perm]
                 orders[e] = sample_idx
-            loss, status = self._trainer.run(orders)
-            self.kernel_ms_ += status['kernel_ms']
-            curve.extend(loss.tolist())
-            if self.verbose:
-                for i, v in enumerate(loss):
-                    print('Iteration %d, loss = %.8f' % (len(curve) - len(loss) + i + 1, v))
+            return state, orders, sample_idx
+
+        curve, status, self.kernel_ms_ = [], dict(stopped=False, n_iter=0, best_loss=np.inf), 0.0
+        planned = 0                                         # epochs whose orders have been drawn
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            m = min(self._chunk, self.max_iter)
+            nxt = pool.submit(draw_chunk, np.arange(n), m) if m > 0 else None
+            while nxt is not None:
+                state, orders, sample_idx = nxt.result()
+                planned += len(orders)
+                m = min(self._chunk, self.max_iter - planned)
+                nxt = pool.submit(draw_chunk, sample_idx, m) if m > 0 else None
+                loss, status = self._trainer.run(orders)
+                self.kernel_ms_ += status['kernel_ms']
+                curve.extend(loss.tolist())
+                if self.verbose:
+                    for i, v in enumerate(loss):
+                        print('Iteration %d, loss = %.8f' % (len(curve) - len(loss) + i + 1, v))
+                if status['stopped']:
+                    if nxt is not None:
+                        nxt.result()                        # let the helper finish before the generator is rewound
+                        nxt = None
+                    rng.set_state(state)
+                    for e in range(status['epochs_done']):
+                        rng.shuffle(np.arange(n))
         self.loss_curve_, self.n_iter_ = curve, status['n_iter']
         self.loss_, self.best_loss_ = (curve[-1] if curve else np.inf), status['best_loss']
         self.t_ = self.n_iter_ * n

@@ -43,10 +43,12 @@ def test_device_fit_matches_sklearn_and_stops_alike():
     from sklearn.neural_network import MLPRegressor
     from so_b200.train_surrogate import DeviceMLPRegressor
     X, y = _data(400, 30, seed=5)
-    kw = dict(activation='relu', learning_rate_init=0.01, alpha=0.1, hidden_layer_sizes=(20,), max_iter=2000, tol=1e-3,
-              random_state=3)
-    ref = MLPRegressor(**kw).fit(X, y)
-    dev = DeviceMLPRegressor(**kw).fit(X, y)
+    kw = dict(activation='relu', learning_rate_init=0.01, alpha=0.1, hidden_layer_sizes=(20,), max_iter=2000, tol=1e-3)
+    rs_ref, rs_dev = np.random.RandomState(3), np.random.RandomState(3)
+    ref = MLPRegressor(random_state=rs_ref, **kw).fit(X, y)
+    dev = DeviceMLPRegressor(random_state=rs_dev, **kw).fit(X, y)
+    # the generator is left where scikit-learn leaves it (the stop fires inside a chunk of prepared epoch orders)
+    assert ref.n_iter_ % 16 != 0 and rs_ref.randint(1 << 30) == rs_dev.randint(1 << 30)
     assert ref.n_iter_ < 2000 and dev.n_iter_ == ref.n_iter_
     np.testing.assert_allclose(dev.loss_curve_, ref.loss_curve_, rtol=1e-8)
     _close(dev, ref.coefs_[0], ref.intercepts_[0], ref.coefs_[1], ref.intercepts_[1][0], rtol=1e-6, atol=1e-10)
