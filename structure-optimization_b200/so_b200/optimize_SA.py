@@ -38,7 +38,8 @@ def default_guard_tol(tables, p_w2_abs_sum, y_scale):
 
 def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0=0.05, cooling='exp', fldr=None,
              n_record=100, prefix='', *, n_chains=1, seed=None, proposals=None, uniforms=None, exact_guard=True,
-             guard_tol=None, gate=True, py2_linear=False, return_stats=False):
+             guard_tol=None, gate=True, py2_linear=False, ladder=None, exchange_every=None, gather_every=None,
+             return_stats=False):
     """
     :param cat:        catalyst (LSC_cat / NH3_cat); its occupancy is the start and is replaced by the result
     :param mode:       'surrogate' or 'analytical' (LSC only)
@@ -49,6 +50,11 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     Extras: n_chains independent chains from the same start (the best final one is kept); seed of the Philox streams
     (default: drawn from Python's global `random`, the generator upstream uses); proposals/uniforms [n_chains, steps]
     to inject the random sequence; exact_guard re-decides near-ties with the fp64 weights.
+    Parallel tempering: `ladder=R` groups the chains into ladders of R temperatures, geometric in
+    [T*e^-5, T] around the schedule's T; every `exchange_every` steps (default: one sweep) adjacent rungs swap
+    temperatures.  Under torch.distributed (one process per GPU) each rank anneals its own n_chains chains, ladders are
+    strided over the ranks, and every rank ends with the same global best structure (NCCL all-gather of one record per
+    rank); `gather_every` steps additionally tracks the best structure seen so far.
     """
     N = len(cat.variable_occs)
     total_steps = n_cycles * N
@@ -77,6 +83,17 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     chains.attach(tables)
     if seed is None:
         seed = random.getrandbits(63)
+    rank, world = _rank_world()
+    chain_id0 = rank * n_chains
+    pt = gather = None
+    if ladder is not None or gather_every is not None or world > 1:
+        from . import parallel
+        if ladder is not None:
+            pt = parallel.ReplicaExchange(chains, ladder=int(ladder), seed=seed, rank=rank, world=world)
+            exchange_every = N if exchange_every is None else int(exchange_every)
+            if exchange_every < 1:
+                raise ValueError('exchange_every must be a positive number of steps')
+        gather = parallel.BestGather(chains, chain_id0, world)
     if (proposals is None) != (uniforms is None):
         raise ValueError('proposals and uniforms must be given together')
     if proposals is not None:
@@ -97,30 +114,64 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     stats = dict(flips=0, accepted=0, guard_fired=0, kernel_ms=0.0, seed=seed)
     t_start = time.time()
     done = 0
-    for b in sorted(set(int(v) for v in steps_to_record if v > 0)):
+    record_at = set(int(v) for v in steps_to_record if v > 0)
+    cuts = set(record_at)
+    if pt is not None:
+        cuts.update(range(exchange_every, total_steps, exchange_every))
+    if gather_every is not None:
+        cuts.update(range(int(gather_every), total_steps, int(gather_every)))
+    swap_round = 0
+    for b in sorted(cuts):
         seg = slice(done, b)
-        st = chains.anneal(temps[seg], step0=done, seed=seed,
+        st = chains.anneal(temps[seg], step0=done, seed=seed, chain_id0=chain_id0,
                            proposals=None if proposals is None else proposals[:, seg],
                            uniforms=None if uniforms is None else uniforms[:, seg],
                            exact_guard=exact_guard, guard_tol=guard_tol or 0.0)
         for k in ('flips', 'accepted', 'guard_fired', 'kernel_ms'):
             stats[k] += st[k]
         done = b
-        OF = chains.objective()
-        step_rec[record_ind] = b                              # (step + 1) of the last step of the segment
-        OF_rec[record_ind] = OF.max() / cat.atoms_per_layer
-        temps_rec[record_ind] = temps[b - 1]
-        record_ind += 1
+        if pt is not None and b % exchange_every == 0 and b < total_steps:
+            pt.round(swap_round, t_ref=max(float(temps[b - 1]), 1e-300))
+            swap_round += 1
+        if gather_every is not None and b % int(gather_every) == 0:
+            gather.gather()
+        if b in record_at:
+            OF = chains.objective()
+            step_rec[record_ind] = b                          # (step + 1) of the last step of the segment
+            OF_rec[record_ind] = OF.max() / cat.atoms_per_layer
+            temps_rec[record_ind] = temps[b - 1]
+            record_ind += 1
     stats['wall_s'] = time.time() - t_start
+    OF = chains.objective()
     best = int(np.argmax(OF)) if len(OF) else 0
     x = chains.get_occupancy(best, 1)[0]
-    stats['best_chain'], stats['OF'] = best, float(OF[best])
+    stats['best_chain'], stats['OF'] = chain_id0 + best, float(OF[best])
+    if gather is not None:
+        # every rank ends with the same structure: the global best of the final states, or an earlier one that was better
+        gather.gather()
+        of_b, cid_b, bits_b = gather.best
+        x = engine.unpack_bits(bits_b[None, :], N)[0]
+        stats['best_chain'], stats['OF'] = int(cid_b), float(of_b)
+        stats['world'], stats['rank'] = world, rank
+    if pt is not None:
+        stats['temperature_swaps'] = int(pt.swapped)
     stats['trajectory'] = np.array([step_rec, OF_rec])
     stats['temperatures'] = temps_rec
     cat.assign_occs([int(v) for v in x])                      # OML/optimize_SA.py:138
     chains.close()
     _save_trajectory(fldr, prefix, step_rec, OF_rec, temps_rec)
     return stats if return_stats else None
+
+
+def _rank_world():
+    """(rank, world) of torch.distributed when this process is one of several (one per GPU), else (0, 1)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
 
 
 def _save_trajectory(fldr, prefix, step_rec, OF_rec, temps_rec):

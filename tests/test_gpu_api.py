@@ -197,6 +197,32 @@ def test_optimize_many_chains_and_files(tmp_path):
     assert cat2.variable_occs == cat.variable_occs
 
 
+def test_optimize_parallel_tempering():
+    """optimize(..., ladder=R): temperature ladders + swap rounds + best-structure record through the drop-in call
+    (single process = world 1; the multi-rank path is scripts/optimize_multi_gpu.py under torchrun)."""
+    from so_b200 import LSC_cat, optimize
+    p = Hp.golden_surrogate(gated=False)
+    sur = duck_surrogate(p)
+    random.seed(2)
+    outs = []
+    for rep in range(2):
+        cat = LSC_cat(12)
+        random.seed(2)
+        cat.randomize(coverage=0.5)
+        x0 = np.array(cat.variable_occs)
+        out = optimize(cat, surrogate=sur, n_cycles=12, T_0=0.05, n_chains=64, seed=11, ladder=8, gather_every=300,
+                       exact_guard=False, return_stats=True)
+        outs.append((list(cat.variable_occs), out))
+    (xa, a), (xb, b) = outs
+    assert xa == xb and a["OF"] == b["OF"] and a["temperature_swaps"] == b["temperature_swaps"] > 0     # deterministic
+    final = S.eval_rate_fp64(p, L.generate_all_translations(np.array(xa), 12))
+    start = S.eval_rate_fp64(p, L.generate_all_translations(x0, 12))
+    assert abs(final - a["OF"]) <= 1e-5 * abs(final) and final > start
+    assert a["flips"] == 12 * 144 * 64 and 0 <= a["best_chain"] < 64
+    with pytest.raises(ValueError):
+        optimize(LSC_cat(12), surrogate=sur, n_cycles=1, n_chains=10, ladder=8)          # chains not a multiple of the ladder
+
+
 def test_optimize_analytical_mode():
     from so_b200 import LSC_cat, optimize
     cat = LSC_cat(12)
