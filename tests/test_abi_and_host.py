@@ -76,3 +76,56 @@ def test_descriptor_offsets_and_tree_flattening():
     assert (descriptor_offsets(49, 96) == L.local_offsets(3)).all()
     with pytest.raises(ValueError):
         descriptor_offsets(50, 12)
+
+
+def test_device_regressor_host_logic_with_stub_trainer(monkeypatch):
+    """DeviceMLPRegressor's host side without a GPU: the Glorot draws, the cumulative epoch shuffles prepared in chunks by
+    a helper thread, and the rewind of the generator when the stop rule fires inside a chunk must reproduce
+    scikit-learn's use of the RandomState.  The device trainer is replaced by the NumPy training oracle."""
+    import warnings
+    from sklearn.neural_network import MLPRegressor
+    from so_b200 import engine
+    from so_b200.train_surrogate import DeviceMLPRegressor
+    from oracle import train as T
+
+    class StubTrainer(object):
+        def __init__(self, X, y, W1, b1, w2, b2, lr, alpha, beta1, beta2, eps, tol, batch_size, n_iter_no_change, device):
+            self.X, self.y, self.kw = np.asarray(X, dtype=np.float64), y, dict(lr=lr, alpha=alpha, tol=tol)
+            self.init, self.orders, self.res = (W1, b1, w2, b2), [], None
+
+        def run(self, orders):
+            before = len(self.orders)
+            self.orders.extend(list(orders))
+            self.res = T.fit_adam(self.X, self.y, init=self.init, orders=self.orders, max_iter=len(self.orders), **self.kw)
+            done = self.res["n_iter"] - before
+            stopped = self.res["n_iter"] < len(self.orders) or self._stop_at_end()
+            return self.res["loss_curve"][before:], dict(epochs_done=done, n_iter=self.res["n_iter"], stopped=stopped,
+                                                         adam_steps=0, best_loss=float(self.res["loss_curve"].min()),
+                                                         kernel_ms=0.0)
+
+        def _stop_at_end(self):      # did the tol rule fire exactly at the last prepared epoch?
+            again = T.fit_adam(self.X, self.y, init=self.init, orders=self.orders + [self.orders[-1]],
+                               max_iter=len(self.orders) + 1, **self.kw)
+            return again["n_iter"] == len(self.orders)
+
+        def get(self):
+            return self.res["W1"], self.res["b1"], self.res["w2"], self.res["b2"]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(engine, "Trainer", StubTrainer)
+    rng = np.random.default_rng(5)
+    X = (rng.random((400, 30)) < 0.5).astype(np.float64)
+    y = np.maximum(X @ (rng.normal(size=30) / np.sqrt(30)), 0) + 0.05 * rng.normal(size=400)
+    y = (y - y.mean()) / y.std()
+    kw = dict(activation='relu', learning_rate_init=0.01, alpha=0.1, hidden_layer_sizes=(20,), max_iter=2000, tol=1e-3)
+    rs_ref, rs_dev = np.random.RandomState(3), np.random.RandomState(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = MLPRegressor(random_state=rs_ref, **kw).fit(X, y)
+        dev = DeviceMLPRegressor(random_state=rs_dev, epochs_per_launch=7, **kw).fit(X, y)
+    assert dev.n_iter_ == ref.n_iter_ and ref.n_iter_ % 7 != 0
+    np.testing.assert_allclose(dev.loss_curve_, ref.loss_curve_, rtol=1e-9)
+    np.testing.assert_allclose(dev.coefs_[0], ref.coefs_[0], rtol=1e-7, atol=1e-11)
+    assert rs_ref.randint(1 << 30) == rs_dev.randint(1 << 30)        # generator left where scikit-learn leaves it
