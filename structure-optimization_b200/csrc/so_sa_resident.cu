@@ -18,6 +18,8 @@
 #include "so_internal.cuh"
 #include <math.h>
 
+#define SO_TREE_SMEM_NODES 2048
+
 namespace {
 
 struct DrawR {
@@ -138,12 +140,14 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
   const SurView &sv = P.sv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d, N = P.N, K = sv.K, KW = (K + 31) >> 5, W = P.W;
-  const int n_tree = GATED ? sv.n_tree : 0;
+  // trees of up to SO_TREE_SMEM_NODES nodes are copied to shared memory, larger ones are walked in global memory (L1/L2)
+  const int n_tree = (GATED && sv.n_tree <= SO_TREE_SMEM_NODES) ? sv.n_tree : 0;
   // shared layout: [W1q: K*HP4 int4][tree: n_tree int4][offsets: K][w2q: HP4 int4] | per warp: [hq: N*HP4 int4][bits W][act W]
   // [path index S: N*KW][active rows of the step: K u32][their positions: K u16]
   int4 *s_W = (int4 *)s_raw;
-  int4 *s_tree = s_W + (size_t)K * HP4;
-  int32_t *s_off = (int32_t *)(s_tree + n_tree);
+  int4 *s_tree_buf = s_W + (size_t)K * HP4;
+  const int4 *s_tree = n_tree ? s_tree_buf : sv.t_packed;
+  int32_t *s_off = (int32_t *)(s_tree_buf + n_tree);
   int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
   unsigned char *s_chain0 = (unsigned char *)(s_w2 + HP4);
   const size_t per_warp = (RES ? (size_t)N * HP4 * 16 : 0) +
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)sv.w2q)[threadIdx.x];
   if (GATED) {
-    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree[i] = sv.t_packed[i];
+    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree_buf[i] = sv.t_packed[i];
   }
   __syncthreads();
   const int part = lane % HP4, rsub = lane / HP4;
@@ -435,12 +439,14 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
   const SurView &sv = P.sv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d, N = P.N, K = sv.K, KW = (K + 31) >> 5, W = P.W;
-  const int n_tree = GATED ? sv.n_tree : 0;
+  // trees of up to SO_TREE_SMEM_NODES nodes are copied to shared memory, larger ones are walked in global memory (L1/L2)
+  const int n_tree = (GATED && sv.n_tree <= SO_TREE_SMEM_NODES) ? sv.n_tree : 0;
   // shared layout: [W1q][tree][offsets][w2q][hq: N*HP4 int4][parts: 2 x TEAM_WARPS x 3 int64][chain id][bits W][act W]
   // [S: N*KW][lists: KW*32 u32][positions: K u16][counts: KW int]
   int4 *s_W = (int4 *)s_raw;
-  int4 *s_tree = s_W + (size_t)K * HP4;
-  int32_t *s_off = (int32_t *)(s_tree + n_tree);
+  int4 *s_tree_buf = s_W + (size_t)K * HP4;
+  const int4 *s_tree = n_tree ? s_tree_buf : sv.t_packed;
+  int32_t *s_off = (int32_t *)(s_tree_buf + n_tree);
   int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
   int4 *hq = s_w2 + HP4;
   long long *s_part = (long long *)(hq + (size_t)N * HP4);
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)sv.w2q)[threadIdx.x];
   if (GATED)
-    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree[i] = sv.t_packed[i];
+    for (int i = threadIdx.x; i < n_tree; i += blockDim.x) s_tree_buf[i] = sv.t_packed[i];
   const int part = lane % HP4, rsub = lane / HP4;
   const bool worker = lane < STRIDE;
   const int4 w2 = worker ? __ldg((const int4 *)sv.w2q + part) : make_int4(0, 0, 0, 0);
@@ -684,11 +690,11 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
 }  // namespace
 
 static size_t shared_tables_bytes(const so_surrogate *s) {
-  const int n_tree = s->gated ? s->n_tree : 0;
+  const int n_tree = (s->gated && s->n_tree <= SO_TREE_SMEM_NODES) ? s->n_tree : 0;
   return (size_t)s->K * s->HP4 * 16 + (size_t)n_tree * 16 + a16((size_t)s->K * 4) + (size_t)s->HP4 * 16;
 }
 static bool shape_ok(const so_surrogate *s, int N) {
-  return !((s->gated ? s->n_tree : 0) > 2048 || s->K > 1024 || s->HP4 > 8 || N > 32767);
+  return !(s->K > 1024 || s->HP4 > 8 || N > 32767);
 }
 
 // Warps per CTA and its shared memory, maximising the resident chains of an SM; false if the state does not fit

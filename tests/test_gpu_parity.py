@@ -279,7 +279,7 @@ def test_sa_gated_full_descriptor(eng, variant):
     _run_sa(eng, 12, Hp.golden_surrogate(gated=True), n_chains=16, steps=1200, seed=24, variant=variant)
 
 
-def _random_tree(K, depth, seed):
+def _random_tree(K, depth, seed, grow=0.8):
     rng = np.random.default_rng(seed)
     feature, thr, left, right, active = [], [], [], [], []
 
@@ -287,7 +287,7 @@ def _random_tree(K, depth, seed):
         i = len(feature)
         feature.append(-2); thr.append(0.0); left.append(-1); right.append(-1); active.append(int(rng.random() < 0.6))
         # uneven depth, plus a few tests that ignore their bit (thr outside [0, 1))
-        if level < depth and (level < 2 or rng.random() < 0.8):
+        if level < depth and (level < 2 or rng.random() < grow):
             feature[i] = int(rng.integers(0, K))
             thr[i] = float(rng.choice([0.5, 0.5, 0.5, 0.5, -1.0, 1.5]))
             left[i] = node(level + 1)
@@ -320,6 +320,16 @@ def test_sa_gated_hot_resident(eng, d, variant):
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=80 + d)
     p.tree = _random_tree(49, 8, seed=100 + d)
     r = _run_sa(eng, d, p, n_chains=24, steps=1500, seed=90 + d, T0=2.0, cooling="const", variant=variant)
+    assert r["acc"].mean() > 0.1
+
+
+@pytest.mark.parametrize("d,variant", [(12, 4), (12, 5), (24, 0)])
+def test_sa_gated_large_tree(eng, d, variant):
+    """A tree too large for shared memory (8,191 nodes > 2,048) is walked in global memory by the same kernels."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=120 + d)
+    p.tree = _random_tree(49, 12, seed=121, grow=1.0)
+    assert len(p.tree["feature"]) == 8191
+    r = _run_sa(eng, d, p, n_chains=12, steps=1200, seed=122 + d, T0=1.0, cooling="const", variant=variant)
     assert r["acc"].mean() > 0.1
 
 
