@@ -234,9 +234,11 @@ def test_optimize_analytical_mode():
     assert LA.eval_struc_rate_anal(np.array(cat.variable_occs), 12) >= start
 
 
-def test_exact_guard_matches_reference_decisions():
+@pytest.mark.parametrize("variant", [0, 1, 4, 5])
+def test_exact_guard_matches_reference_decisions(variant):
     """With the near-tie guard on, decisions follow the ORIGINAL fp64 weights even where the fixed-point delta is
-    within the guard band of the threshold; the guard must fire and the result must equal the faithful oracle."""
+    within the guard band of the threshold; the guard must fire and the result must equal the faithful oracle
+    (every gated kernel: 0 = auto, 1 = row-per-lane, 4 = resident warp per chain, 5 = resident CTA per chain)."""
     from so_b200 import engine
     d, steps, n_chains = 12, 1440, 4
     z = np.load(os.path.join(Hp.GOLDEN, "sa_d12_golden.npz"))
@@ -246,7 +248,7 @@ def test_exact_guard_matches_reference_decisions():
     ch.set_occupancy(z["x0"])
     ch.attach(Hp.tables_from_params(lat, p))
     stats, acc = ch.anneal(z["temps"], proposals=z["prop"], uniforms=z["u"], want_accept=True, exact_guard=True,
-                           guard_tol=5e-3)                            # wide band: the exact path takes many decisions
+                           guard_tol=5e-3, variant=variant)           # wide band: the exact path takes many decisions
     assert stats["guard_fired"] > 10
     assert (acc.astype(bool) == z["gated_faithful_accept"]).all()
     assert (ch.get_occupancy() == z["gated_faithful_x"]).all()
