@@ -231,7 +231,7 @@ int so_chains_destroy(so_chains *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->bits_dev); cudaFree(c->hq_dev); cudaFree(c->hi_dev); cudaFree(c->lo_dev); cudaFree(c->nact_dev);
-  cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch);
+  cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch); cudaFree(c->temps_dev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -717,9 +717,20 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   if (a->proposals)
     for (size_t i = 0; i < nc * ns; ++i)
       SO_REQUIRE(a->proposals[i] >= 0 && a->proposals[i] < L->N, "proposal %zu = %d out of range", i, a->proposals[i]);
-  DevBuf d_temps, d_prop, d_uni, d_acc;
-  SO_TRY(d_temps.alloc(ns * 8));
-  SO_CUDA(cudaMemcpyAsync(d_temps.p, a->temps, ns * 8, cudaMemcpyHostToDevice, c->stream));
+  DevBuf d_prop, d_uni, d_acc;
+  if (c->temps_cap < ns * 8) {
+    cudaFree(c->temps_dev);
+    c->temps_dev = nullptr;
+    c->temps_cap = 0;
+    const size_t want = std::max<size_t>(ns * 8, 1 << 16);
+    if (cudaMalloc(&c->temps_dev, want) != cudaSuccess) {
+      cudaGetLastError();
+      so_set_error("cudaMalloc(%zu bytes) failed for the temperature schedule", want);
+      return SO_ENOMEM;
+    }
+    c->temps_cap = want;
+  }
+  SO_CUDA(cudaMemcpyAsync(c->temps_dev, a->temps, ns * 8, cudaMemcpyHostToDevice, c->stream));
   if (a->proposals) {
     SO_TRY(d_prop.alloc(nc * ns * 4));
     SO_TRY(d_uni.alloc(nc * ns * 4));
@@ -731,7 +742,7 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   SaParams P;
   P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
   P.bits = c->bits_dev; P.hq = c->hq_dev; P.hi = c->hi_dev; P.lo = c->lo_dev; P.nact = c->nact_dev;
-  P.tscale = c->tscale_dev; P.temps = d_temps.as<double>();
+  P.tscale = c->tscale_dev; P.temps = c->temps_dev;
   P.step0 = a->step0; P.n_steps = a->n_steps; P.seed = a->seed; P.chain_id0 = a->chain_id0;
   P.proposals = a->proposals ? d_prop.as<int32_t>() : nullptr;
   P.uniforms = a->uniforms ? d_uni.as<float>() : nullptr;

@@ -63,6 +63,8 @@ struct so_chains {
   int64_t xch_cap;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
+  double *temps_dev;                    // schedule staging of so_anneal (grow-only: many short launches per optimize())
+  size_t temps_cap;
   mutable uint32_t *gate_scratch;       // path index of the resident warps of the cached-gate kernel (so_sa_resident.cu)
   mutable size_t gate_scratch_bytes;
   CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
