@@ -23,19 +23,20 @@ def random_tree(K, depth, rng):
 
 
 d, n = 96, int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+depth = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 lat = engine.Lattice(d, "NH3")
 off = engine.local_offsets(3)
 W1, b1, w2, b2 = glorot_mlp(off, 20, 0)
 sweep = d * d
 temps = exp_schedule(0.05, 5 * sweep)
 for gated, variant in ((False, 0), (True, 0), (True, 1)):
-    tree = random_tree(49, 8, np.random.default_rng(0)) if gated else None
+    tree = random_tree(49, depth, np.random.default_rng(0)) if gated else None
     tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=tree)
     ch = engine.Chains(lat, n)
     ch.randomize(1, 0.5)
     ch.attach(tab)
     for i in range(3):          # sweeps 0, 1, 2 of a 5-sweep exponential schedule: acceptance falls as in a real run
         st = ch.anneal(temps[i * sweep:(i + 1) * sweep], seed=2, step0=i * sweep, variant=variant)
-        print("gated=%s variant=%d sweep %d: %.3e flip-evals/s (kernel %.1f ms, accept %.3f)" % (
-            gated, variant, i, st["flips"] / st["kernel_ms"] * 1e3, st["kernel_ms"], st["accepted"] / st["flips"]), flush=True)
+        print("depth %d gated=%s variant=%d sweep %d: %.3e flip-evals/s (kernel %.1f ms, accept %.3f)" % (
+            depth, gated, variant, i, st["flips"] / st["kernel_ms"] * 1e3, st["kernel_ms"], st["accepted"] / st["flips"]), flush=True)
     ch.close()

@@ -27,7 +27,8 @@ d, n = 96, 16384
 lat = engine.Lattice(d, "NH3")
 off = engine.local_offsets(3)
 W1, b1, w2, b2 = glorot_mlp(off, 20, 0)
-tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=random_tree(49, 8, np.random.default_rng(0)))
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=random_tree(49, depth, np.random.default_rng(0)))
 ch = engine.Chains(lat, n); ch.randomize(1, 0.5); ch.attach(tab)
 sweep = d * d
 temps = exp_schedule(0.05, 5 * sweep)
