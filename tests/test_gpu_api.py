@@ -345,3 +345,16 @@ def test_optimize_on_nh3_cat_default_lattice():
     assert abs(out["OF"] - ref) <= 1e-5 * abs(ref)
     cat.graph_to_KMClattice()
     assert cat.KMC_lat.site_type_inds == ST.nh3_export(o["x"][0], d)
+
+
+def test_active_learning_loop_runs():
+    """The reference's learn -> anneal -> evaluate loop (drivers/Online_learn_main.py) through the OML module paths:
+    database, device-fitted regressor + tree gate, SA on the GPU, analytical re-evaluation (scripts/active_learning_loop.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("al_loop", os.path.join(os.path.dirname(Hp.GOLDEN), "..", "scripts",
+                                                                          "active_learning_loop.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hist = mod.main(iterations=2, n_strucs=8, n_cycles=20, verbose=False)
+    assert len(hist) == 2 and all(np.isfinite(v) for row in hist for v in row)
+    assert hist[0][1] > hist[0][2]          # the first surrogate optimum beats every random island structure of the database
