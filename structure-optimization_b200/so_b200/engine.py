@@ -252,6 +252,10 @@ class Chains(object):
     # -- annealing
     def anneal(self, temps, step0=0, seed=0, chain_id0=0, proposals=None, uniforms=None, want_accept=False,
                exact_guard=False, guard_tol=0.0, variant=0):
+        """so_anneal: len(temps) Metropolis steps for every chain (the loop of OML/optimize_SA.py:59-132).
+        temps[s] is the schedule temperature of step step0 + s (times the chain's tscale); draws come from Philox streams
+        keyed by (seed, chain_id0 + chain, step) or from proposals / uniforms [n_chains, steps]; want_accept returns the
+        accept/reject bytes.  variant selects a kernel for cross-checks (0 = automatic, see include/so_b200.h)."""
         temps = np.ascontiguousarray(temps, dtype=np.float64)
         ns = len(temps)
         a = B.AnnealArgs()
