@@ -1,3 +1,5 @@
+"""Few-to-many chains on the 12x12 lattice: CTA-per-chain kernel (variant 5) against warp-per-chain (variant 4);
+the break-even (about two chains per SM) is what so_team_ok() encodes."""
 import sys; sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/structure-optimization_b200'); sys.path.insert(0, '/root/repo/tests')
 from so_b200 import engine
 import helpers as Hp
