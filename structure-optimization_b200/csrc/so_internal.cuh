@@ -145,7 +145,7 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st);
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);
-bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem);
+bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem, int min_warps_per_sm = 8);
 bool so_gate_index_ok(const so_surrogate *s, int N, int W);
 bool so_team_ok(const so_surrogate *s, int N, int W, long long n_chains, int n_sm);
 int so_launch_anneal_team(const so_chains *c, const SaParams &P, cudaStream_t st);

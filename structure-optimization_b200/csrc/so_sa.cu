@@ -591,10 +591,10 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
   // small lattices: the whole chain state stays in shared memory for the launch (so_sa_resident.cu)
   // few chains on a small lattice: a CTA per chain (latency); many: a warp per chain (throughput)
-  if ((P.variant == 0 || P.variant == 5) && so_team_ok(s, P.N, P.W, P.variant == 5 ? 1 : P.n_chains, n_sm) &&
-      so_resident_plan(s, P.N, P.W, nullptr, nullptr))
+  if ((P.variant == 0 || P.variant == 5) && so_team_ok(s, P.N, P.W, P.variant == 5 ? 1 : P.n_chains, n_sm))
     return so_launch_anneal_team(c, P, st);
-  if ((P.variant == 0 || P.variant == 4) && so_resident_plan(s, P.N, P.W, nullptr, nullptr))
+  if ((P.variant == 0 && so_resident_plan(s, P.N, P.W, nullptr, nullptr)) ||
+      (P.variant == 4 && so_resident_plan(s, P.N, P.W, nullptr, nullptr, 1)))
     return so_launch_anneal_resident(c, P, st);
   // gated, large lattice: cached gates + path index, only the active rows are read (so_sa_resident.cu)
   if ((P.variant == 0 || P.variant == 3) && so_gate_index_ok(s, P.N, P.W)) return so_launch_anneal_gate_index(c, P, st);

@@ -699,7 +699,7 @@ static bool shape_ok(const so_surrogate *s, int N) {
 
 // Warps per CTA and its shared memory, maximising the resident chains of an SM; false if the state does not fit
 // (or the tree is too large to share).
-bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out) {
+bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out, int min_warps_per_sm) {
   const size_t kSmemSM = 228 * 1024, kSmemCTA = 227 * 1024;
   const int KW = (s->K + 31) / 32;
   if (!shape_ok(s, N)) return false;
@@ -715,7 +715,7 @@ bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_
     if (per_sm * w > 64) per_sm = 64 / w;
     if (per_sm * w > best_total) { best_total = per_sm * w; best_w = w; best_smem = smem; }
   }
-  if (best_total < 8) return false;       // too few resident chains to keep an SM busy: the global-memory kernels win
+  if (best_total < min_warps_per_sm) return false;   // too few resident chains to keep an SM busy: the global-memory kernels win
   if (warps_out) *warps_out = best_w;
   if (smem_out) *smem_out = best_smem;
   return true;
@@ -776,7 +776,7 @@ int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_
   int n_sm = 0, warps = 0;
   size_t smem = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-  if (!so_resident_plan(s, P.N, P.W, &warps, &smem)) { so_set_error("resident kernel: state does not fit"); return SO_EINVAL; }
+  if (!so_resident_plan(s, P.N, P.W, &warps, &smem, 1)) { so_set_error("resident kernel: state does not fit"); return SO_EINVAL; }
   const int per_sm = (int)((228 * 1024) / (smem + 1024));
   long long want = (P.n_chains + warps - 1) / warps;
   int blocks = (int)(want < (long long)n_sm * per_sm ? want : (long long)n_sm * per_sm);
