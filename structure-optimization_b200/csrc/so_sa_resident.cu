@@ -731,7 +731,10 @@ static size_t team_smem_bytes(const so_surrogate *s, int N, int W) {
 bool so_team_ok(const so_surrogate *s, int N, int W, long long n_chains, int n_sm) {
   // pays only while the SMs are otherwise idle: measured break-even at about two chains per SM (the four warps of a
   // team repeat the draws and the decision, so a team costs roughly twice the issue slots of a single warp)
-  return shape_ok(s, N) && n_chains <= 2LL * n_sm && team_smem_bytes(s, N, W) <= 100 * 1024;
+  // (up to one CTA per SM with all of its shared memory: a single chain on a 48x48 lattice still runs from shared memory)
+  const size_t smem = team_smem_bytes(s, N, W);
+  if (!shape_ok(s, N) || smem > 227 * 1024) return false;
+  return n_chains <= (smem <= 113 * 1024 ? 2LL : 1LL) * n_sm;
 }
 
 int so_launch_anneal_team(const so_chains *c, const SaParams &P, cudaStream_t st) {
