@@ -298,12 +298,13 @@ def _random_tree(K, depth, seed, grow=0.8):
                 right=np.array(right, np.int32), active=np.array(active, np.uint8))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("d,T0", [(24, 0.05), (24, 2.0), (40, 0.3)])
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("d,T0", [(24, 0.05), (24, 2.0), (40, 0.3), (48, 1.0)])
 def test_sa_gated_local_large_lattice(eng, d, T0, variant):
-    """Tree gate on a lattice too large for shared memory: the cached-gate kernel (variant 0: gate bits + path index,
-    only active rows read) and the row-per-lane kernel (variant 1) against the oracle; hot runs exercise the index
-    upkeep on accept."""
+    """Tree gate on lattices too large for the warp-per-chain resident kernel: 20 chains run on the CTA-per-chain
+    kernel (variant 0, state in up to 227 KB of shared memory), the cached-gate kernel with global state (variant 3:
+    gate bits + path index, only active rows read) and the row-per-lane kernel (variant 1), all against the oracle;
+    hot runs exercise the index upkeep on accept."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=60 + d)
     p.tree = _random_tree(49, 7, seed=d)
     r = _run_sa(eng, d, p, n_chains=20, steps=1500, seed=70 + d, T0=T0, variant=variant,
@@ -323,7 +324,7 @@ def test_sa_gated_hot_resident(eng, d, variant):
     assert r["acc"].mean() > 0.1
 
 
-@pytest.mark.parametrize("d,variant", [(12, 4), (12, 5), (24, 0)])
+@pytest.mark.parametrize("d,variant", [(12, 4), (12, 5), (24, 0), (24, 3)])
 def test_sa_gated_large_tree(eng, d, variant):
     """A tree too large for shared memory (8,191 nodes > 2,048) is walked in global memory by the same kernels."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=120 + d)
