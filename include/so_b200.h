@@ -144,9 +144,12 @@ typedef struct so_anneal_stats {
   int64_t accepted;
   int64_t guard_fired;
   float kernel_ms;           /* CUDA-event time of the annealing kernel(s) only     */
+  int kernel_id;             /* which kernel the dispatch chose (so_kernel_name)    */
 } so_anneal_stats;
 
 int so_anneal(so_chains *c, const so_anneal_args *args, so_anneal_stats *stats);
+/* name of the kernel behind so_anneal_stats.kernel_id ("sa_window_kernel", "sa_resident_kernel", ...)   */
+const char *so_kernel_name(int kernel_id);
 /* per-chain temperature scale (parallel-tempering rung), default 1.0                                      */
 int so_set_tscale(so_chains *c, int64_t chain0, int64_t n, const double *tscale);
 int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale);

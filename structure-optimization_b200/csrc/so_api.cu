@@ -752,7 +752,8 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   P.gate_scratch = nullptr;
   P.sv = make_view(c->sur);
   SO_CUDA(cudaEventRecord(c->ev0, c->stream));
-  SO_TRY(so_launch_anneal(c, P, c->stream));
+  int kernel_id = SO_K_NONE;
+  SO_TRY(so_launch_anneal(c, P, c->stream, &kernel_id));
   SO_CUDA(cudaEventRecord(c->ev1, c->stream));
   if (a->accept_out) SO_CUDA(cudaMemcpyAsync(a->accept_out, d_acc.p, nc * ns, cudaMemcpyDeviceToHost, c->stream));
   SO_CUDA(cudaStreamSynchronize(c->stream));
@@ -763,8 +764,22 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
     stats->accepted = (int64_t)cnt[1];
     stats->guard_fired = (int64_t)cnt[2];
     SO_CUDA(cudaEventElapsedTime(&stats->kernel_ms, c->ev0, c->ev1));
+    stats->kernel_id = kernel_id;
   }
   return SO_OK;
+}
+
+const char *so_kernel_name(int kernel_id) {
+  switch (kernel_id) {
+    case SO_K_TEAM: return "sa_team_kernel";
+    case SO_K_RESIDENT: return "sa_resident_kernel";
+    case SO_K_GATE_INDEX: return "sa_resident_kernel<RES=false> (cached gates, state in HBM)";
+    case SO_K_WINDOW: return "sa_window_kernel";
+    case SO_K_FLAT: return "sa_flat_kernel";
+    case SO_K_GATED: return "sa_gated_kernel";
+    case SO_K_ANALYTICAL: return "lsc_anneal_kernel";
+    default: return "none";
+  }
 }
 
 int so_set_tscale(so_chains *c, int64_t chain0, int64_t n, const double *tscale) {
@@ -849,6 +864,7 @@ int so_anneal_analytical(so_chains *c, const so_anneal_args *a, so_anneal_stats 
     stats->flips = (int64_t)(nc * ns);
     stats->accepted = (int64_t)cnt[1];
     SO_CUDA(cudaEventElapsedTime(&stats->kernel_ms, c->ev0, c->ev1));
+    stats->kernel_id = SO_K_ANALYTICAL;
   }
   return SO_OK;
 }

@@ -141,7 +141,10 @@ int so_launch_objective(const so_surrogate *s, const long long *hi, const long l
                         double *of_dev, cudaStream_t st);
 int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_dev, uint8_t *active_dev,
                         double *rate_dev, cudaStream_t st);
-int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st);
+// kernel ids reported in so_anneal_stats.kernel_id (names: so_kernel_name)
+enum { SO_K_NONE = 0, SO_K_TEAM = 1, SO_K_RESIDENT = 2, SO_K_GATE_INDEX = 3, SO_K_WINDOW = 4, SO_K_FLAT = 5, SO_K_GATED = 6,
+       SO_K_ANALYTICAL = 7 };
+int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int *kernel_id);
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);

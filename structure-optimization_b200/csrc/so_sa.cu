@@ -584,7 +584,9 @@ static int launch_flat(const SaParams &P, size_t smem, int blocks, cudaStream_t 
   return SO_OK;
 }
 
-int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
+int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int *kernel_id) {
+  int kid_local = 0;
+  int &kid = kernel_id ? *kernel_id : kid_local;
   const so_surrogate *s = c->sur;
   int dev = c->lat->device, n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -592,17 +594,19 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
   // small lattices: the whole chain state stays in shared memory for the launch (so_sa_resident.cu)
   // few chains on a small lattice: a CTA per chain (latency); many: a warp per chain (throughput)
   if ((P.variant == 0 || P.variant == 5) && so_team_ok(s, P.N, P.W, P.variant == 5 ? 1 : P.n_chains, n_sm))
-    return so_launch_anneal_team(c, P, st);
+    return kid = SO_K_TEAM, so_launch_anneal_team(c, P, st);
   if ((P.variant == 0 && so_resident_plan(s, P.N, P.W, nullptr, nullptr)) ||
       (P.variant == 4 && so_resident_plan(s, P.N, P.W, nullptr, nullptr, 1)))
-    return so_launch_anneal_resident(c, P, st);
+    return kid = SO_K_RESIDENT, so_launch_anneal_resident(c, P, st);
   // gated, large lattice: cached gates + path index, only the active rows are read (so_sa_resident.cu)
-  if ((P.variant == 0 || P.variant == 3) && so_gate_index_ok(s, P.N, P.W)) return so_launch_anneal_gate_index(c, P, st);
+  if ((P.variant == 0 || P.variant == 3) && so_gate_index_ok(s, P.N, P.W))
+    return kid = SO_K_GATE_INDEX, so_launch_anneal_gate_index(c, P, st);
   if (!s->gated && (P.variant == 0 || P.variant == 3) && s->win_ok && s->K * s->HP4 <= 256 &&
       so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 113 * 1024) {
-    return so_launch_anneal_window(c, P, st);
+    return kid = SO_K_WINDOW, so_launch_anneal_window(c, P, st);
   }
   if (!s->gated && P.variant != 1) {
+    kid = SO_K_FLAT;
     int Q = s->K * s->HP4;
     size_t tab = (size_t)Q * 16 + (size_t)s->K * 4;
     bool tab_smem = tab <= kSmemTabLimit;
@@ -618,6 +622,7 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st) {
       return launch_flat<HP4_, 0, false>(P, smem, blocks, st);
     });
   } else {
+    kid = SO_K_GATED;
     size_t smem = (size_t)4 * P.W * 4;
     long long want = (P.n_chains + 3) / 4;
     int blocks = (int)(want < (long long)n_sm * 8 ? want : (long long)n_sm * 8);

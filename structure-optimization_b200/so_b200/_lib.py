@@ -26,7 +26,7 @@ class AnnealArgs(C.Structure):
 
 class AnnealStats(C.Structure):
     _fields_ = [("flips", C.c_int64), ("accepted", C.c_int64), ("guard_fired", C.c_int64),
-                ("kernel_ms", C.c_float)]
+                ("kernel_ms", C.c_float), ("kernel_id", C.c_int)]
 
 
 class TrainParams(C.Structure):
@@ -71,6 +71,7 @@ PROTOTYPES = {
     "so_score_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_u32p, c_f64p, c_i32p, c_i32p]),
     "so_eval_rows": (C.c_int, [C.c_void_p, C.c_int64, c_u8p, c_u8p, c_f64p]),
     "so_anneal": (C.c_int, [C.c_void_p, C.POINTER(AnnealArgs), C.POINTER(AnnealStats)]),
+    "so_kernel_name": (C.c_char_p, [C.c_int]),
     "so_set_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
     "so_get_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
     "so_lsc_analytical": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p, c_f64p]),

@@ -33,11 +33,15 @@ class SlabTemplate(object):
     def get_chemical_symbols(self):
         return list(self._symbols)
 
-    def get_scaled_positions(self):
+    def get_scaled_positions(self, wrap=True):
+        """Fractional coordinates; like ASE, the two periodic (in-plane) axes are wrapped into [0, 1)."""
         inv = np.linalg.inv(self._cell[:2, :2])
         out = np.zeros_like(self._pos)
         out[:, :2] = self._pos[:, :2] @ inv
         out[:, 2] = self._pos[:, 2] / self._cell[2, 2]
+        if wrap:
+            out[:, :2] %= 1.0
+            out[:, :2] %= 1.0
         return out
 
 
@@ -215,7 +219,7 @@ class dynamic_cat(object):
         """OML/dynamic_cat.py:366-401 renders the slab with ASE (png / xsd / povray): visualisation is out of scope."""
         raise NotImplementedError('show() needs ASE rendering, which is outside the B200 hot path')
 
-    # ---- out-of-scope leftovers kept for API completeness (GA / distance metric, OML/dynamic_cat.py:188-220,404-437)
+    # ---- GA operators / distance metric (OML/dynamic_cat.py:188-220,404-437; SURVEY 8f-4), host side: O(N) per call
     def geo_crossover(self, x1, x2, pt1=1, pt2=1):
         x_bounds = [random.random() for i in range(pt1)]
         y_bounds = [random.random() for i in range(pt2)]

@@ -273,7 +273,8 @@ class Chains(object):
         a.exact_guard, a.guard_tol, a.variant = int(bool(exact_guard)), float(guard_tol), int(variant)
         st = B.AnnealStats()
         B.check(self.lib.so_anneal(self.h, C.byref(a), C.byref(st)))
-        stats = dict(flips=st.flips, accepted=st.accepted, guard_fired=st.guard_fired, kernel_ms=st.kernel_ms)
+        stats = dict(flips=st.flips, accepted=st.accepted, guard_fired=st.guard_fired, kernel_ms=st.kernel_ms,
+                     kernel=self.lib.so_kernel_name(st.kernel_id).decode())
         return (stats, acc) if want_accept else stats
 
     def lsc_analytical(self, chain0=0, n=None, site_rates=True):

@@ -95,25 +95,39 @@ class KMCLattice(object):
         self.cart_coords = None
         self.frac_coords = None
         self.neighbor_list = []
+        self.cell_list = []          # per pair: 'self' | 'north' | 'northeast' | 'east' | 'southeast'
 
     def set_cart_coords(self, cart_coords):
         self.cart_coords = np.asarray(cart_coords, dtype=np.float64).reshape(-1, 2)
         self.frac_coords = self.cart_coords @ np.linalg.inv(np.asarray(self.lattice_matrix))
 
+    # Zacros names the periodic image the second site of a pair sits in (lattice_input.dat "neighboring_structure"):
+    # image shift in units of the two cell vectors (a, b) -> keyword
+    CELLS = ((0, 0, 'self'), (0, 1, 'north'), (1, 1, 'northeast'), (1, 0, 'east'), (1, -1, 'southeast'))
+
     def Build_neighbor_list(self, cut=3.0):
-        """Pairs [i, j], i < j, of sites closer than `cut` under the periodic cell (minimum image)."""
-        self.neighbor_list = []
+        """zacros_wrapper.Lattice.Build_neighbor_list: pairs [s1, s2] of sites closer than `cut`, with the cell the
+        second site is taken from in `cell_list`: 'self' (s1 < s2), or s2 displaced by +b ('north'), +a+b
+        ('northeast'), +a ('east'), +a-b ('southeast').  Every periodic pair appears once; a pair that crosses the
+        cell edge the other way is listed with its sites exchanged."""
+        self.neighbor_list, self.cell_list = [], []
         n = len(self.site_type_inds)
         if n == 0:
             return
-        cell = np.asarray(self.lattice_matrix)
-        f = self.frac_coords
-        for i in range(n):
-            df = f[i + 1:] - f[i]
-            df -= np.round(df)
-            dist = np.sqrt(((df @ cell) ** 2).sum(1))
-            for j in np.nonzero(dist < cut)[0]:
-                self.neighbor_list.append([i, int(i + 1 + j)])
+        a, b = np.asarray(self.lattice_matrix, dtype=np.float64)
+        c = self.cart_coords
+        found = []
+        for na, nb, name in self.CELLS:
+            shift = na * a + nb * b
+            dist = np.sqrt(((c[None, :, :] + shift - c[:, None, :]) ** 2).sum(2))       # [s1, s2]
+            s1, s2 = np.nonzero(dist < cut)
+            for i, j in zip(s1.tolist(), s2.tolist()):
+                if name != 'self' or i < j:
+                    found.append((i, j, name))
+        order = {name: k for k, (_, _, name) in enumerate(self.CELLS)}
+        found.sort(key=lambda t: (t[0], t[1], order[t[2]]))
+        self.neighbor_list = [[i, j] for i, j, _ in found]
+        self.cell_list = [name for _, _, name in found]
 
     def Write_lattice_input(self, fldr):
         """lattice_input.dat in the layout of zacros_input/lattice_input.dat:1-37."""
@@ -133,6 +147,6 @@ class KMCLattice(object):
             for x, y in (self.frac_coords if n else []):
                 f.write('\t %.5f \t%.5f \n' % (x, y))
             f.write('\nneighboring_structure \t # site-neighsite cell\n')
-            for i, j in self.neighbor_list:
-                f.write('\t %d-%d self \n' % (i + 1, j + 1))
+            for (i, j), cell in zip(self.neighbor_list, self.cell_list):
+                f.write('\t %d-%d %s \n' % (i + 1, j + 1, cell))
             f.write('end_neighboring_structure\n\nend_lattice\n')

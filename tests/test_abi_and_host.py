@@ -129,3 +129,60 @@ def test_device_regressor_host_logic_with_stub_trainer(monkeypatch):
     np.testing.assert_allclose(dev.loss_curve_, ref.loss_curve_, rtol=1e-9)
     np.testing.assert_allclose(dev.coefs_[0], ref.coefs_[0], rtol=1e-7, atol=1e-11)
     assert rs_ref.randint(1 << 30) == rs_dev.randint(1 << 30)        # generator left where scikit-learn leaves it
+
+
+def test_lattice_input_writer_regenerates_reference_fixture(tmp_path):
+    """Write_lattice_input byte for byte: the reference's zacros_input/lattice_input.dat rebuilt from its own 14 sites
+    (layer-3 atoms of the 12x12 slab) -- compared with the file itself where the reference tree is present, and with its
+    SHA-256 everywhere (the file is not copied into this repo)."""
+    import hashlib
+    import json
+    from so_b200.graph import KMCLattice
+    from oracle import lattice as L
+    import helpers as Hp
+    d = 12
+    sites = [(5, 1), (11, 1), (0, 2), (4, 2), (1, 7), (8, 7), (2, 8), (8, 8), (3, 9), (6, 9), (1, 10), (2, 11), (7, 11), (10, 11)]
+    pos = L.slab_positions(d)[3 * d * d:4 * d * d, :2]
+    lat = KMCLattice()
+    lat.lattice_matrix = L.cell_vectors(d)
+    lat.site_type_names = ['top_Ni', 'top_corner_Ni', 'top_edge_Ni']
+    lat.site_type_inds = [2] * len(sites)
+    lat.set_cart_coords([pos[i2 * d + i1] for i1, i2 in sites])
+    lat.Build_neighbor_list(cut=2.77 + 0.1)
+    fx = json.load(open(os.path.join(Hp.GOLDEN, "lattice_input_fixture.json")))
+    assert [[i + 1, j + 1] for i, j in lat.neighbor_list] == fx["neighbor_pairs"] and lat.cell_list == ['self', 'self']
+    lat.Write_lattice_input(str(tmp_path))
+    got = open(os.path.join(str(tmp_path), 'lattice_input.dat'), 'rb').read()
+    assert hashlib.sha256(got).hexdigest() == '8d51532be1b424aba1920d194a34fa7057137c6352ad2d1ff03a37626bee3ae8'
+    ref = '/root/reference/zacros_input/lattice_input.dat'
+    if os.path.exists(ref):
+        assert got == open(ref, 'rb').read()
+
+
+def test_kmc_neighbour_cells_across_the_periodic_edge():
+    """Pairs that cross the cell edge carry Zacros' direction keyword (second site displaced into that image)."""
+    from so_b200.graph import KMCLattice
+    from oracle import lattice as L
+    d = 6
+    pos = L.slab_positions(d)[3 * d * d:4 * d * d, :2]
+    lat = KMCLattice()
+    lat.lattice_matrix = L.cell_vectors(d)
+    lat.site_type_names = ['top_Ni', 'top_edge_Ni']
+    lat.site_type_inds = [1] * (d * d)
+    lat.set_cart_coords(pos)
+    lat.Build_neighbor_list(cut=2.77 + 0.1)
+    assert len(lat.neighbor_list) == 3 * d * d                     # every site has 6 neighbours, each pair once
+    a, b = lat.lattice_matrix
+    shift = dict(self=0 * a, north=b, northeast=a + b, east=a, southeast=a - b)
+    seen = set()
+    for (i, j), cell in zip(lat.neighbor_list, lat.cell_list):
+        assert abs(np.linalg.norm(pos[j] + shift[cell] - pos[i]) - L.D_NN) < 1e-9
+        assert cell != 'self' or i < j
+        seen.add(frozenset((i, j)))
+    assert len(seen) == 3 * d * d
+    assert set(lat.cell_list) == {'self', 'north', 'east', 'southeast'} or 'northeast' in lat.cell_list
+    v = lambda i1, i2: (i2 % d) * d + i1 % d
+    k = lat.neighbor_list.index([v(5, 2), v(0, 2)])                # (5,2) -> (6,2) wraps along the first cell vector
+    assert lat.cell_list[k] == 'east'
+    k = lat.neighbor_list.index([v(3, 5), v(3, 0)])                # (3,5) -> (3,6) wraps along the second
+    assert lat.cell_list[k] == 'north'

@@ -90,7 +90,7 @@ def test_lsc_graph_to_kmc_lattice():
         cat.graph_to_KMClattice()
         types_, sites = ST.lsc_export(x, d)
         assert cat.KMC_lat.site_type_inds == types_ and cat.var_ind_kmc_sites == sites
-        assert sorted(map(tuple, cat.KMC_lat.neighbor_list)) == sorted(LA.kmc_neighbor_pairs(sites, d))
+        assert sorted(tuple(sorted(p)) for p in cat.KMC_lat.neighbor_list) == sorted(LA.kmc_neighbor_pairs(sites, d))
         full = ST.lsc_types(x, d)[0]
         for v in range(0, 144, 7):
             assert cat.defected_graph.node[432 + v]['site_type'] == (int(full[v]) or None)
