@@ -9,9 +9,12 @@ One "step" = one sweep (N = 9216 Metropolis steps) of every chain.  Workload (BA
 d = 96, 65,536 chains per GPU, reference-width MLP 49 -> 20 -> 1 on the 7x7 local descriptor
 (OML/dynamic_cat.py:325-341), random-init weights (sklearn Glorot bounds), gate off, geometric ('exp') cooling
 from T_0 = 0.05, x0 ~ Bernoulli(0.5), Philox4x32-10 proposals/uniforms.  Chains shard across ranks with no
-data-path collective; at N > 1 a best-structure all-gather (NCCL) runs after every sweep inside the timed region,
-and --pt adds the parallel-tempering swap round of BASELINE configs[4] (fixed-temperature ladders strided across
-the GPUs, all-gather of the objectives + a deterministic swap kernel).
+data-path collective; at N > 1 a best-structure all-gather (NCCL) runs after every sweep inside the timed region.
+--gpus 8 runs BASELINE configs[4] by default (524,288 chains, parallel tempering: ladders of 8 fixed temperatures
+geometric in [T0*e^-5, T0] strided across the GPUs, a swap round after every sweep = all-gather of the objectives + a
+deterministic swap kernel, best-structure all-gather every 10 sweeps); --pt / --no-pt force either mode at any N.  After
+the timed region the PT run checks itself (temperature multiset preserved, every rank holds the same temperature
+table, one extra swap round equals oracle/exchange.py on sampled ladders) and prints the result next to the value.
 """
 import argparse
 import json
@@ -159,9 +162,22 @@ def run_reference(a):
         "gpu_launches": 0}))
 
 
+def use_pt(a):
+    """BASELINE configs[4] (parallel tempering) is the 8-GPU configuration; configs[3] (cooling) everything else."""
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    return bool(a.pt) if a.pt is not None else world == 8
+
+
 def workload_config(a, cores_note=None):
-    cfg = {"workload": "BASELINE configs[3]: %dx%d periodic NiPt lattice, %d chains per GPU, 49->20->1 MLP surrogate "
-                       "(7x7 local descriptor, random-init, gate off), exp cooling T0=%g" % (a.d, a.d, a.chains, T0),
+    if use_pt(a):
+        wl = ("BASELINE configs[4]: %dx%d periodic NiPt lattice, %d chains per GPU (x%d GPUs), 49->20->1 MLP surrogate "
+              "(7x7 local descriptor, random-init, gate off), parallel tempering: ladders of %d fixed temperatures geometric "
+              "in [T0*e^-5, T0], T0=%g, strided across the GPUs; swap round after every sweep, best-structure all-gather "
+              "every %d sweeps" % (a.d, a.d, a.chains, a.gpus, a.ladder, T0, a.gather_every or 10))
+    else:
+        wl = ("BASELINE configs[3]: %dx%d periodic NiPt lattice, %d chains per GPU, 49->20->1 MLP surrogate "
+              "(7x7 local descriptor, random-init, gate off), exp cooling T0=%g" % (a.d, a.d, a.chains, T0))
+    cfg = {"workload": wl,
            "lattice": "%dx%d" % (a.d, a.d), "chains_per_gpu": a.chains, "descriptor": "local7x7", "hidden": H,
            "step": "one sweep = %d Metropolis steps per chain" % (a.sweep_steps if a.sweep_steps > 0 else a.d * a.d),
            "l2_policy": "working set (%.1f GB of per-chain state) >> 126 MB L2; no flush needed" % (
@@ -170,6 +186,85 @@ def workload_config(a, cores_note=None):
     if cores_note:
         cfg["note"] = cores_note
     return cfg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def pt_self_check(pt, ch, tscale_initial, rounds_done, rank, world, dist, n_sample=64):
+    """Untimed tail of a parallel-tempering run.  (1) the multiset of temperatures is the initial ladder's; (2) every
+    rank holds the same temperature table and its chains carry their slice of it; (3) one EXTRA swap round equals
+    oracle/exchange.py (the checker -- not timed, not shipped) on `n_sample` ladders spread over the whole table."""
+    import torch
+    n = ch.n
+    ts = pt.tscale_all
+    ok_multiset = bool(torch.equal(torch.sort(ts)[0], torch.sort(tscale_initial)[0]))
+    # order-sensitive 64-bit checksum of the table, compared across ranks
+    bits = ts.view(torch.int64)
+    mult = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64) * 2654435761
+    chk = (bits * mult).sum().reshape(1)
+    if dist is not None:
+        allchk = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        ok_same = all(int(c) == int(chk) for c in allchk)
+    else:
+        ok_same = True
+    ok_local = bool(np.array_equal(ch.get_tscale(), ts[rank * n:(rank + 1) * n].cpu().numpy()))
+    before = ts.cpu().numpy().copy()
+    pt.round(rounds_done, t_ref=T0)                      # the extra round (all ranks take part in its all-gather)
+    after = pt.tscale_all.cpu().numpy()
+    of_all = pt.of_all.cpu().numpy()
+    ok_oracle, n_swapped = None, None
+    if rank == 0:
+        from oracle import exchange as OX
+        n_global = world * n
+        n_lad = n_global // pt.ladder
+        lads = np.unique(np.linspace(0, n_lad - 1, min(n_sample, n_lad)).astype(np.int64))
+        want = OX.exchange_round(of_all, before, world, n, pt.ladder, rounds_done & 1, pt.seed, rounds_done, T0, ladders=lads)
+        pos = np.concatenate([[OX.gathered_position(l * pt.ladder + i, world, n) for i in range(pt.ladder)] for l in lads])
+        ok_oracle = bool(np.array_equal(want[pos], after[pos]))
+        n_swapped = int((before[pos] != after[pos]).sum())
+    if dist is not None:
+        flags = torch.tensor([int(ok_multiset), int(ok_local)], device=ts.device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        ok_multiset, ok_local = bool(flags[0]), bool(flags[1])
+    return {"temperature_multiset_preserved": ok_multiset, "tscale_table_identical_on_all_ranks": ok_same,
+            "local_chains_carry_their_slice": ok_local, "extra_round_equals_oracle_exchange": ok_oracle,
+            "sampled_ladders": int(min(n_sample, (world * n) // pt.ladder)), "temperatures_swapped_in_sample": n_swapped,
+            "swap_rounds_run": int(rounds_done)}
+
+
+def accept_sweeps(ch, a, N, chain_id0, peak, targets=(0.5, 0.2, 0.05)):
+    """The hot kernel where flips ARE accepted: one full sweep of every chain at a CONSTANT temperature chosen (by
+    bisection on short launches) so that the accept fraction is about each target; same shape as the headline.
+    Returns [{target, T, accept_fraction, ms, value, bytes_per_flip, achieved GB/s, frac}]."""
+    out = []
+    probe = max(32, min(N, 256))
+    step0 = 10 ** 9                                  # Philox counters far away from the timed region
+    lo_T, hi_T = 1e-4, 1e3
+    for tgt in targets:
+        lo, hi = lo_T, hi_T
+        T = np.sqrt(lo * hi)
+        for it in range(14):
+            T = np.sqrt(lo * hi)
+            st = ch.anneal(np.full(probe, T), step0=step0, seed=a.seed + 1, chain_id0=chain_id0)
+            step0 += probe
+            frac = st["accepted"] / max(st["flips"], 1)
+            if abs(frac - tgt) <= 0.02 * max(tgt, 0.1):
+                break
+            if frac > tgt:
+                hi = T
+            else:
+                lo = T
+        for rep in range(2):                          # one sweep to equilibrate at T, one measured
+            st = ch.anneal(np.full(N, T), step0=step0, seed=a.seed + 1, chain_id0=chain_id0)
+            step0 += N
+        af = st["accepted"] / max(st["flips"], 1)
+        b_alg = 4.0 * K_WIN * H * (1.0 + af) + 15.0 + 4.0 * af
+        ach = st["flips"] * b_alg / (st["kernel_ms"] * 1e-3) / 1e9
+        out.append({"target": tgt, "T": float(T), "accept_fraction": af, "ms": st["kernel_ms"],
+                    "value": st["flips"] / (st["kernel_ms"] * 1e-3), "bytes_per_flip": b_alg, "achieved": ach,
+                    "frac": ach / peak, "kernel": st["kernel"]})
+        hi_T = T                                      # next (smaller) target: colder
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -203,12 +298,17 @@ def run_gpu(a):
     chain_id0 = rank * n_local
 
     from so_b200 import parallel
-    gather = parallel.BestGather(ch, chain_id0, world) if (world > 1 or a.pt) else None
+    want_pt = use_pt(a)
+    gather = parallel.BestGather(ch, chain_id0, world) if (world > 1 or want_pt) else None
+    gather_every = a.gather_every or (10 if want_pt else 1)
     pt = None
-    if a.pt:      # BASELINE configs[4]: fixed-temperature ladders (geometric in [T0*e^-5, T0]) + swap round per sweep
+    if want_pt:   # BASELINE configs[4]: fixed-temperature ladders (geometric in [T0*e^-5, T0]) + swap round per sweep
         pt = parallel.ReplicaExchange(ch, ladder=a.ladder, seed=a.seed, rank=rank, world=world)
+        tscale_initial = pt.tscale_all.clone()
         temps_all = np.full(total_sweeps * N, T0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    n_gathers = [0]
 
     def sweep(s):
         st = ch.anneal(temps_all[s * N:(s + 1) * N], step0=s * N, seed=a.seed, chain_id0=chain_id0)
@@ -217,8 +317,9 @@ def run_gpu(a):
             ev0.record()
             if pt is not None:
                 pt.round(s, t_ref=T0)
-            if gather is not None:
+            if gather is not None and ((s + 1) % gather_every == 0 or s == total_sweeps - 1):
                 gather.gather()
+                n_gathers[0] += 1
             ev1.record()
             ev1.synchronize()
             coll_ms = ev0.elapsed_time(ev1)
@@ -232,12 +333,15 @@ def run_gpu(a):
     for s in range(a.warmup):
         sweep(s)
     barrier()
+    n_gathers[0] = 0
     kern_ms, coll_ms, flips, accepted = 0.0, 0.0, 0, 0
+    kernel_name = None
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for s in range(a.warmup, total_sweeps):
             st, cm = sweep(s)
             kern_ms += st["kernel_ms"]
+            kernel_name = st["kernel"]                               # what the dispatch launched (so_anneal_stats.kernel_id)
             coll_ms += cm
             flips += st["flips"]
             accepted += st["accepted"]
@@ -280,6 +384,7 @@ def run_gpu(a):
                "h2d_bytes_per_step": int(bits_host.nbytes + N * 8), "d2h_bytes_per_step": int(bits_host.nbytes + of.nbytes),
                "steps": a.e2e_steps}
 
+    pt_check = pt_self_check(pt, ch, tscale_initial, total_sweeps, rank, world, dist) if pt is not None else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -308,9 +413,9 @@ def run_gpu(a):
         "data": "synthetic", "config": workload_config(a),
         "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e,
         # SA kernel per sweep (+ arg-max kernel of the all-gather, + objective/decision/commit kernels of a swap round)
-        "gpu_launches": a.steps * (1 + (1 if gather is not None else 0) + (3 if pt is not None else 0)),
+        "gpu_launches": a.steps * (1 + (3 if pt is not None else 0)) + n_gathers[0],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sa_window_kernel<5,9>",
+                     "traffic": traffic, "kernel": kernel_name,
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "launch_ms": kern_ms / a.steps},
     }
@@ -319,6 +424,9 @@ def run_gpu(a):
         line["best_structure"] = {"of": gather.best[0], "chain": gather.best[1]}
     if pt is not None:
         line["config"]["parallel_tempering"] = {"ladder": a.ladder, "swaps_local_rank0": pt.swapped}
+        line["pt_self_check"] = pt_check
+    if world == 1 and pt is None and a.accept_sweep:
+        line["accept_sweep"] = accept_sweeps(ch, a, N, chain_id0, peak)
     if world == 1 and a.cpu_flips > 0:
         cores = os.cpu_count() or 1
         v, wall = cpu_reference_rate(d, a.cpu_flips, cores, total_sweeps * N)
@@ -439,9 +547,13 @@ def main():
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
     ap.add_argument("--sweep-steps", type=int, default=0, help="Metropolis steps per chain per bench step (0 = d*d)")
     ap.add_argument("--seed", type=int, default=2026)
-    ap.add_argument("--pt", action="store_true", help="parallel tempering (BASELINE configs[4]): fixed ladders + swaps")
+    ap.add_argument("--pt", dest="pt", action="store_true", default=None,
+                    help="parallel tempering (BASELINE configs[4]); default: on at --gpus 8, off otherwise")
+    ap.add_argument("--no-pt", dest="pt", action="store_false")
+    ap.add_argument("--gather-every", type=int, default=0, help="best-structure all-gather period in sweeps (0 = 10 with PT, 1 without)")
     ap.add_argument("--ladder", type=int, default=8, help="parallel-tempering ladder size")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--accept-sweep", type=int, default=1, help="1: also time one sweep at accept fractions 0.5/0.2/0.05")
     ap.add_argument("--cpu-flips", type=int, default=3000, help="Metropolis steps per core for the CPU baseline (0 = skip)")
     ap.add_argument("--ref-flips", type=int, default=1000, help="Metropolis steps per core per bench step, --impl reference")
     a = ap.parse_args()

@@ -13,7 +13,7 @@ def gathered_position(g, world, n_local):
     return (g % world) * n_local + g // world
 
 
-def exchange_round(of_all, tscale_all, world, n_local, ladder, parity, seed, rnd, t_ref):
+def exchange_round(of_all, tscale_all, world, n_local, ladder, parity, seed, rnd, t_ref, ladders=None):
     """Returns the new tscale array (all-gather layout [world][n_local]).  Global chain g = i*world + rank; ladders
     are `ladder` consecutive global ids; rungs ranked by temperature (hottest first, ties by global id); adjacent
     rungs (r, r+1), r = parity (mod 2), swap temperatures with probability min(1, exp[(OF_a-OF_b)(1/T_b-1/T_a)])."""
@@ -22,7 +22,7 @@ def exchange_round(of_all, tscale_all, world, n_local, ladder, parity, seed, rnd
     new = ts.copy()
     n_global = world * n_local
     seed = int(seed)
-    for lad in range(n_global // ladder):
+    for lad in (range(n_global // ladder) if ladders is None else [int(v) for v in ladders]):   # `ladders`: a sample
         pos = [gathered_position(lad * ladder + i, world, n_local) for i in range(ladder)]
         order = sorted(range(ladder), key=lambda i: (-ts[pos[i]], i))
         for r in range(parity, ladder - 1, 2):

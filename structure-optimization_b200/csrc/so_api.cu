@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -99,6 +100,14 @@ int so_lattice_create(int d, int kind, int device, so_lattice **out) {
   SO_REQUIRE(d >= 4 && d <= 1024, "lattice edge d=%d out of range [4,1024] (closed-form typing needs d >= 4)", d);
   SO_REQUIRE(kind == SO_KIND_LSC || kind == SO_KIND_NH3, "unknown catalyst kind %d", kind);
   SO_CUDA(cudaSetDevice(device));
+  {
+    // The SA state is read in 560-byte runs that start on 16-byte boundaries: with the default 64-byte L2 fetch
+    // granule every run drags in ~48 bytes it does not need.  Ask for 32-byte fills (a hint the platform may
+    // clamp); SO_L2_FETCH_GRANULARITY = 0 leaves the default, 32 / 64 / 128 select a value.
+    const char *e = getenv("SO_L2_FETCH_GRANULARITY");
+    const int want = e ? atoi(e) : 32;
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want) != cudaSuccess) cudaGetLastError();
+  }
   so_lattice *L = new (std::nothrow) so_lattice();
   if (!L) { so_set_error("out of host memory"); return SO_ENOMEM; }
   L->d = d; L->N = d * d; L->W = (L->N + 31) / 32; L->kind = kind; L->device = device;

@@ -7,12 +7,13 @@
 //     path, SASS UBLKCP) into a per-warp ring of shared-memory stages, completion on an mbarrier per stage;
 //   * proposals are known ahead of time (counter-based Philox), so the copies for step s+STAGES-1 are issued while
 //     step s computes: STAGES-1 windows per warp are in flight and the HBM latency is off the critical path;
-//   * an accepted flip writes the updated window back with bulk-async stores from the same stage buffer.
+//   * an accepted flip writes the updated window back with one tensor-TMA store from the same stage buffer.
 //     Rare hazards (the window of a prefetched step overlaps a flip accepted after the prefetch was issued, or a
 //     store still in flight) are detected exactly and resolved by draining the stores and re-fetching;
 //   * Philox and the injected-sequence loads are evaluated lane-parallel for 32 steps at a time; the warp sum uses
 //     three REDUX.SUM on 21-bit limbs; exp() runs in fp64 only when an fp32 pre-filter cannot decide.
 #include "so_window_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -28,7 +29,13 @@ __device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_
   return metropolis_cold(delta, T, u, exact_guard, tol);
 }
 
-template <int HP4, int NSLOTS>
+// COMMIT selects how an accepted flip is written back: 0 = updated in the shared-memory stage + one tensor-TMA store
+// (production); 1 = straight from registers with st.global.cg + fence.proxy.async.global, nothing ever waits on the write
+// (SO_WIN_COMMIT=1); 2 = as 1 without the proxy fence (timing experiment only).  Measured on one box, 65,536 chains
+// (profiles/r02_commit_ab.txt): at accept fractions 0.93 / 0.54 / 0.21 the TMA store takes 954 / 711 / 521 ms per sweep,
+// the register store 1001 / 769 / 576 ms, with or without the fence -- the write path is not latency bound, the nine
+// STG.128 + address arithmetic per accepted flip cost more issue slots than one UTMASTG.
+template <int HP4, int NSLOTS, int COMMIT>
 __global__ void __launch_bounds__(WARPS * 32, 2)
     sa_window_kernel(SaParams P, WinGeom g, const int4 *__restrict__ Wst, const __grid_constant__ CUtensorMap tmap) {
   constexpr int STAGES = 3;
@@ -61,9 +68,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
   fence_async_smem();
   __syncthreads();
 
+  // NSLOTS == 0: generic instantiation (slot count from the geometry, loops not unrolled) for shapes other than the
+  // 7x7 / 20-unit headline shape
+  const int nslots = NSLOTS ? NSLOTS : g.nslots;
   const int4 w2 = lane < STRIDE ? s_w2[lane % HP4] : make_int4(0, 0, 0, 0);   // idle lanes re-read data with weight 0
   // every slot but the last stays inside the padded stage; the last one is clamped onto a zero-weight padding entry
-  const int last_off = min(lane + STRIDE * (NSLOTS - 1), stage_i4 - 1) - lane;
+  const int last_off = min(lane + STRIDE * (nslots - 1), stage_i4 - 1) - lane;
   const uint32_t stage_bytes = (uint32_t)Q * 16, stage_pitch = (uint32_t)stage_i4 * 16;
   const uint32_t stage0 = smem_u32(s_stage), bar0 = smem_u32(s_bar);
   uint32_t phase_bits = 0;                          // parity of each stage's mbarrier (bit i)
@@ -93,7 +103,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     // pipeline registers: draws of the steps whose windows are in flight
     int f_a = 0, f_b = 0;
     float u_a = 0.f, u_b = 0.f, t_a = 0.f, t_b = 0.f;
-    int hist0 = -1, hist1 = -1, pend_f = -1;        // flips accepted at steps s-1, s-2; flip whose stores may be in flight
+    int hist0 = -1, hist1 = -1;                     // flips accepted at steps s-1, s-2 (their windows were prefetched earlier)
+    int pend_f = -1;                                // COMMIT == 0: flip whose TMA store may still be in flight
     int slot = 1;                                   // stage of step s (s starts at -(STAGES-1) = -2)
 
     for (long long s = -(STAGES - 1); s < P.n_steps; ++s) {
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         t_q = __shfl_sync(SO_FULL, batch_tf, (int)(sp & 31));
         const int pslot = slot == 0 ? STAGES - 1 : slot - 1;
         const int q1 = pk1(f_q), q2 = pk2(f_q);
-        if (pend_f >= 0 && near_cyclic(q1, pk1(pend_f), gL - 1, d) && near_cyclic(q2, pk2(pend_f), gseg - 1, d)) {
+        if (COMMIT == 0 && pend_f >= 0 && near_cyclic(q1, pk1(pend_f), gL - 1, d) && near_cyclic(q2, pk2(pend_f), gseg - 1, d)) {
           bulk_wait_all();                          // the store of that region may still be in flight
           pend_f = -1;
           __syncwarp();
@@ -141,10 +152,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         mbar_wait(bar0 + slot * 8, (phase_bits >> slot) & 1u);
         phase_bits ^= (1u << slot);
         int4 *stg = s_stage + slot * stage_i4 + lane;
-        if (stale) {
-          bulk_wait_all();                          // lane 0: every store it issued is complete and visible
-          pend_f = -1;
-          __syncwarp();
+        if (stale) {                                // the writers' stores are ordered before this by their __syncwarp
+          if (COMMIT == 0) {
+            bulk_wait_all();                        // lane 0: every store it issued is complete and visible
+            pend_f = -1;
+            __syncwarp();
+          }
           reload_window_cold(stg - lane, hq, f1, f2, gb1, gb2, gL, Q, d, HP4, lane);
           __syncwarp();
         }
@@ -153,8 +166,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         const int4 *Wl = (xbit ? s_Wn : s_Wp) + lane;
         int Dx = 0, Dy = 0, Dz = 0, Dw = 0;
 #pragma unroll
-        for (int it = 0; it < NSLOTS; ++it) {
-          const int off = (it == NSLOTS - 1) ? last_off : STRIDE * it;
+        for (int it = 0; it < nslots; ++it) {
+          const int off = (it == nslots - 1) ? last_off : STRIDE * it;
           const int4 h = stg[off];
           const int4 w = Wl[off];
           Dx += max(h.x + w.x, 0) - max(h.x, 0);
@@ -192,32 +205,58 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
           }
         }
         if (accept) {
-          asm volatile("" ::: "memory");            // re-read the stage rather than keeping updated values live
+          if constexpr (COMMIT == 0) {
+            asm volatile("" ::: "memory");            // re-read the stage rather than keeping updated values live
 #pragma unroll
-          for (int it = 0; it < NSLOTS; ++it) {
-            const int q = lane + STRIDE * it;
-            if (lane < STRIDE && q < Q) {
-              int4 h = stg[STRIDE * it];
-              const int4 w = Wl[STRIDE * it];
-              h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
-              stg[STRIDE * it] = h;
+            for (int it = 0; it < nslots; ++it) {
+              const int q = lane + STRIDE * it;
+              if (lane < STRIDE && q < Q) {
+                int4 h = stg[STRIDE * it];
+                const int4 w = Wl[STRIDE * it];
+                h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
+                stg[STRIDE * it] = h;
+              }
             }
+            fence_async_smem();                       // generic-proxy writes -> visible to the bulk (async proxy) store
+            bulk_wait_all();                          // at most one flip's stores in flight (lane 0 owns the groups)
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t src = stage0 + slot * stage_pitch;
+              if (use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d)
+                tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
+              else
+                boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4);
+              bulk_commit();
+              s_bits[f >> 5] ^= (1u << (f & 31));
+              // the stage is re-used by the prefetch issued at the next step: the store must have read it by then
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            pend_f = fp;
+          } else {
+            // commit: h + dw of every slot goes from registers to the chain's state in global memory
+            {
+              const int part = lane % HP4, pbase = lane / HP4;
+#pragma unroll
+              for (int it = 0; it < nslots; ++it) {
+                const int q = lane + STRIDE * it;
+                if (lane < STRIDE && q < Q) {
+                  int4 h = stg[STRIDE * it];
+                  const int4 w = Wl[STRIDE * it];
+                  h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
+                  const int p = pbase + (STRIDE / HP4) * it;          // site of the window, row-major over (p2, p1)
+                  const int p2 = p / gL, p1 = p - p2 * gL;
+                  int r1 = f1 - gb1 + p1, r2 = f2 - gb2 + p2;
+                  r1 += r1 < 0 ? d : 0; r1 -= r1 >= d ? d : 0;
+                  r2 += r2 < 0 ? d : 0; r2 -= r2 >= d ? d : 0;
+                  __stcg(hq + (size_t)(r2 * d + r1) * HP4 + part, h);
+                }
+              }
+            }
+            // generic-proxy stores -> later async-proxy (TMA) reads of the same bytes: each writer fences, the
+            // __syncwarp at the end of the step orders lane 0's next prefetch after all of them
+            if (COMMIT == 1) asm volatile("fence.proxy.async.global;" ::: "memory");
+            if (lane == 0) s_bits[f >> 5] ^= (1u << (f & 31));
           }
-          fence_async_smem();                       // generic-proxy writes -> visible to the bulk (async proxy) store
-          bulk_wait_all();                          // at most one flip's stores in flight (lane 0 owns the groups)
-          __syncwarp();
-          if (lane == 0) {
-            const uint32_t src = stage0 + slot * stage_pitch;
-            if (use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d)
-              tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
-            else
-              boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4);
-            bulk_commit();
-            s_bits[f >> 5] ^= (1u << (f & 31));
-            // the stage is re-used by the prefetch issued at the next step: the store must have read it by then
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-          pend_f = fp;
           lo += acc & SO_SPLIT_MASK;
           hi += (acc >> SO_SPLIT_BITS) + (lo >> SO_SPLIT_BITS);
           lo &= SO_SPLIT_MASK;
@@ -232,7 +271,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
       f_a = f_q; u_a = u_q; t_a = t_q;
       slot = slot + 1 == STAGES ? 0 : slot + 1;
     }
-    bulk_wait_all();
+    if (COMMIT == 0) bulk_wait_all();
     __syncwarp();
     for (int w = lane; w < P.W; w += 32) bits_g[w] = s_bits[w];
     if (lane == 0) {
@@ -256,31 +295,43 @@ size_t so_window_smem_bytes(int Q, int W, int stages) {
   return i4 * 16 + words * 4 + (size_t)WARPS * stages * 8 + 16;
 }
 
-template <int HP4, int NSLOTS>
+template <int HP4, int NSLOTS, int COMMIT>
 static int launch_window(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks, cudaStream_t st) {
-  auto kern = sa_window_kernel<HP4, NSLOTS>;
+  auto kern = sa_window_kernel<HP4, NSLOTS, COMMIT>;
   SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)c->sur->Wst_dev, c->tmap);
   SO_CUDA(cudaGetLastError());
   return SO_OK;
 }
 
+static int window_commit_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("SO_WIN_COMMIT");
+    mode = e ? atoi(e) : 0;
+    if (mode < 0 || mode > 2) mode = 0;
+  }
+  return mode;
+}
+
+template <int HP4, int NSLOTS>
+static int launch_window_commit(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks,
+                                cudaStream_t st) {
+  switch (window_commit_mode()) {
+    case 2: return launch_window<HP4, NSLOTS, 2>(c, P, g, smem, blocks, st);
+    case 1: return launch_window<HP4, NSLOTS, 1>(c, P, g, smem, blocks, st);
+    default: return launch_window<HP4, NSLOTS, 0>(c, P, g, smem, blocks, st);
+  }
+}
+
+// the shape every BASELINE configuration with a local descriptor uses (7x7 window, 17..20 hidden units) is fully
+// unrolled; any other window / width runs the generic instantiation of its HP4
 template <int HP4>
 static int launch_window_hp4(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks,
                              cudaStream_t st) {
-  switch (g.nslots) {
-    case 1: return launch_window<HP4, 1>(c, P, g, smem, blocks, st);
-    case 2: return launch_window<HP4, 2>(c, P, g, smem, blocks, st);
-    case 3: return launch_window<HP4, 3>(c, P, g, smem, blocks, st);
-    case 4: return launch_window<HP4, 4>(c, P, g, smem, blocks, st);
-    case 5: return launch_window<HP4, 5>(c, P, g, smem, blocks, st);
-    case 6: return launch_window<HP4, 6>(c, P, g, smem, blocks, st);
-    case 7: return launch_window<HP4, 7>(c, P, g, smem, blocks, st);
-    case 8: return launch_window<HP4, 8>(c, P, g, smem, blocks, st);
-    case 9: return launch_window<HP4, 9>(c, P, g, smem, blocks, st);
-    case 10: return launch_window<HP4, 10>(c, P, g, smem, blocks, st);
-    default: so_set_error("window too large for the pipelined kernel"); return SO_EINVAL;
-  }
+  if (g.nslots > 10) { so_set_error("window too large for the pipelined kernel"); return SO_EINVAL; }
+  if (HP4 == 5 && g.nslots == 9) return launch_window_commit<5, 9>(c, P, g, smem, blocks, st);
+  return launch_window<HP4, 0, 0>(c, P, g, smem, blocks, st);
 }
 
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st) {

@@ -81,9 +81,8 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     chains = engine.Chains(lattice, n_chains)
     chains.set_occupancy(np.repeat(x0[None, :], n_chains, axis=0))
     chains.attach(tables)
-    if seed is None:
-        seed = random.getrandbits(63)
     rank, world = _rank_world()
+    seed = _shared_seed(seed, rank, world)
     chain_id0 = rank * n_chains
     pt = gather = None
     if ladder is not None or gather_every is not None or world > 1:
@@ -105,6 +104,17 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
         scaler = getattr(surrogate, 'Y_scaler', None)
         guard_tol = default_guard_tol(tables, w2sum, float(scaler.scale_[0]) if scaler is not None else 1.0)
 
+    try:
+        return _anneal_and_record(cat, chains, tables, temps, T_0, total_steps, steps_to_record, step_rec, OF_rec, temps_rec,
+                                  proposals, uniforms, exact_guard, guard_tol, seed, chain_id0, rank, world, pt, gather,
+                                  exchange_every, gather_every, fldr, prefix, return_stats, N)
+    finally:
+        chains.close()                                        # also when a launch raises: no device state outlives the call
+
+
+def _anneal_and_record(cat, chains, tables, temps, T_0, total_steps, steps_to_record, step_rec, OF_rec, temps_rec, proposals,
+                       uniforms, exact_guard, guard_tol, seed, chain_id0, rank, world, pt, gather, exchange_every,
+                       gather_every, fldr, prefix, return_stats, N):
     OF = chains.objective()
     record_ind = 0
     step_rec[record_ind] = 0
@@ -158,9 +168,22 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     stats['trajectory'] = np.array([step_rec, OF_rec])
     stats['temperatures'] = temps_rec
     cat.assign_occs([int(v) for v in x])                      # OML/optimize_SA.py:138
-    chains.close()
     _save_trajectory(fldr, prefix, step_rec, OF_rec, temps_rec)
     return stats if return_stats else None
+
+
+def _shared_seed(seed, rank, world):
+    """The Philox key of a run.  seed=None draws one from Python's global `random` (the generator upstream uses); under
+    torch.distributed EVERY rank must hold the same key -- the parallel-tempering swap decisions are recomputed on each
+    rank from it -- so rank 0's value (given or drawn) is broadcast."""
+    if seed is None:
+        seed = random.getrandbits(63)
+    if world > 1:
+        import torch.distributed as dist
+        box = [int(seed) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        seed = box[0]
+    return int(seed)
 
 
 def _rank_world():

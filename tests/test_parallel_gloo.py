@@ -60,3 +60,44 @@ def test_layout_helpers():
     of = np.array([1.0, 3.0, 3.0, 2.0])
     cid = np.array([9, 7, 4, 1])
     assert P.pick_best(of, cid, np.arange(8).reshape(4, 2))[:2] == (3.0, 4)      # tie -> lowest chain id
+
+
+def _seed_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    from so_b200 import optimize_SA as O
+    random.seed(1000 + rank)                                  # the ranks' own generators disagree ...
+    drawn = O._shared_seed(None, rank, world)                 # ... the key they anneal and swap with must not
+    given = O._shared_seed(5 + rank, rank, world)             # a per-rank argument is overridden by rank 0's as well
+    out[rank] = (drawn, given, O._rank_world())
+    dist.destroy_process_group()
+
+
+def test_every_rank_uses_the_same_philox_key():
+    """Parallel-tempering swap decisions are recomputed on every rank from the run's seed: with seed=None each process
+    would draw its own; optimize() broadcasts rank 0's."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_seed_worker, args=(world, 29617, out), nprocs=world, join=True)
+        r0, r1 = out[0], out[1]
+    assert r0[0] == r1[0] and r0[1] == r1[1] == 5
+    assert r0[2] == (0, 2) and r1[2] == (1, 2)
+    import random
+    random.seed(1000)
+    assert r0[0] == random.getrandbits(63)                    # rank 0's draw from the global generator, as upstream seeds
+
+
+def test_exchange_oracle_ladder_subset_equals_full_round():
+    from oracle import exchange as OX
+    rng = np.random.default_rng(4)
+    world, n_local, ladder = 2, 32, 8
+    of = rng.normal(size=world * n_local)
+    ts = np.exp(-5.0 * ((np.arange(world * n_local) // 1) % ladder) / (ladder - 1))
+    full = OX.exchange_round(of, ts, world, n_local, ladder, 1, 77, 3, 0.05)
+    part = OX.exchange_round(of, ts, world, n_local, ladder, 1, 77, 3, 0.05, ladders=[1, 5])
+    pos = [OX.gathered_position(l * ladder + i, world, n_local) for l in (1, 5) for i in range(ladder)]
+    assert (full[pos] == part[pos]).all() and sorted(full.tolist()) == sorted(ts.tolist())
+    rest = np.setdiff1d(np.arange(world * n_local), pos)
+    assert (part[rest] == ts[rest]).all()
