@@ -154,6 +154,15 @@ const char *so_kernel_name(int kernel_id);
 int so_set_tscale(so_chains *c, int64_t chain0, int64_t n, const double *tscale);
 int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale);
 
+/* ---- checkpoint / resume.  The reference's SA is not resumable (its "checkpoint" is the database folder,
+ *      OML/KMC_handler.py:37-42); here a run continues bit for bit from (bits, tscale, step, seed) because the draws are
+ *      counter based and the first-layer state is an exact function of the bits.  so_chains_save writes bits + tscale +
+ *      the exact objective sums of all chains with the caller's step counter and seed; so_chains_load restores them
+ *      into a handle of the same shape, rebuilds the state and verifies the sums (SO_EINVAL: wrong shape / not a
+ *      checkpoint / written with another surrogate).  step / seed may be NULL.                                */
+int so_chains_save(so_chains *c, const char *path, int64_t step, uint64_t seed);
+int so_chains_load(so_chains *c, const char *path, int64_t *step, uint64_t *seed);
+
 /* ---- analytical objective of the LSC toy model.
  *      so_lsc_analytical: LSC_cat.compute_site_rates_lsc / eval_struc_rate_anal (OML/LSC_cat.py:248-316) of the current
  *      occupancies of chains [chain0, chain0+n): site_rates[n][N] and/or struct_rate[n] (either may be NULL).
@@ -185,7 +194,7 @@ int so_exchange(so_chains *c, int rank, int world, int ladder, int parity, uint6
 /* ---- regressor training on the device (replaces MLPRegressor(...).fit of OML/train_surrogate.py:141-152) ----------
  * The K -> H -> 1 ReLU MLP fitted by mini-batch Adam exactly as scikit-learn runs it (squared loss / 2 +
  * alpha / 2 |coefs|^2 / batch; one Adam step per batch; stop when the epoch loss has not improved by tol for more than
- * n_iter_no_change epochs), fp64, whole optimiser state in the shared memory of one persistent CTA.
+ * n_iter_no_change epochs), fp64, optimiser state in the distributed shared memory of one persistent thread-block cluster of 8 CTAs.
  *   X [n_rows][K] 0/1 descriptor rows (anything else: SO_EINVAL), y [n_rows] scaled targets, W1 [K][H] / b1 [H] /
  *   w2 [H] / b2 initial parameters (e.g. sklearn's Glorot draws).  so_trainer_run() advances n_epochs epochs (or until
  *   the stop rule fires); orders [n_epochs][n_rows] is the sample order of each epoch (batches are consecutive slices

@@ -14,7 +14,7 @@ def build(force=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
+    cmd = ["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("gcc failed:\n" + res.stdout + res.stderr)

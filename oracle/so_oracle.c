@@ -145,5 +145,109 @@ int oracle_anneal_fixed(int d, int K, int Hp, const int32_t *offsets, const int3
   return failed ? -1 : 0;
 }
 
+/* ---- the reference's fp64 rule with its ORIGINAL weights (no fixed point): decision oracle for full-size runs ----------
+ * Same loop as above (OML/optimize_SA.py:59-132) with delta = sum over the K affected rows of
+ * g'(y'*sigma + mu) - g(y*sigma + mu), y = w2 . relu(h) + b2 (OML/train_surrogate.py:40-54), h kept per chain in fp64 and
+ * updated on accept.  delta equals the reference's OF_new - OF up to fp64 rounding (the reference subtracts two full
+ * sums).  margin = |exp(delta/T) - u| of every decision taken in the Metropolis branch; per chain the minimum and the
+ * number of decisions with margin < margin_thr are returned so that callers can state how close any tie was. */
+static int gate_of_fp(int n_tree, const int32_t *feature, const double *thr, const int32_t *left, const int32_t *right,
+                      const uint8_t *active, const int32_t *offsets, const uint8_t *x, int d, int r1, int r2, int flip) {
+  if (n_tree == 0) return 1;
+  int node = 0;
+  while (feature[node] >= 0) {
+    int f = feature[node];
+    int v = wrapi(r2 + offsets[2 * f + 1], d) * d + wrapi(r1 + offsets[2 * f], d);
+    int bit = x[v] ^ (v == flip);
+    node = ((double)bit <= thr[node]) ? left[node] : right[node];
+  }
+  return active[node];
+}
+
+int oracle_anneal_fp64(int d, int K, int H, const int32_t *offsets, const double *W1, const double *b1, const double *w2,
+                       double b2, double sigma, double mu, int n_tree, const int32_t *feature, const double *thr,
+                       const int32_t *left, const int32_t *right, const uint8_t *active, int64_t n_chains,
+                       int64_t n_steps, uint8_t *x, const double *temps, const double *tscale, const int32_t *prop,
+                       const float *u, double margin_thr, uint8_t *accept_out, double *min_margin_out,
+                       int64_t *n_below_out, double *of_out) {
+  const int N = d * d;
+  int failed = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t ch = 0; ch < n_chains; ++ch) {
+    double *h = (double *)malloc((size_t)N * H * sizeof(double));
+    if (!h) { failed = 1; continue; }
+    uint8_t *xc = x + ch * N;
+    for (int r = 0; r < N; ++r) {
+      int r1 = r % d, r2 = r / d;
+      double *hr = h + (size_t)r * H;
+      for (int j = 0; j < H; ++j) hr[j] = b1[j];
+      for (int k = 0; k < K; ++k) {
+        int v = wrapi(r2 + offsets[2 * k + 1], d) * d + wrapi(r1 + offsets[2 * k], d);
+        if (xc[v])
+          for (int j = 0; j < H; ++j) hr[j] += W1[(size_t)k * H + j];
+      }
+    }
+    const double ts = tscale ? tscale[ch] : 1.0;
+    double min_margin = INFINITY;
+    int64_t n_below = 0;
+    for (int64_t s = 0; s < n_steps; ++s) {
+      const double T = ts * temps[s];
+      const int f = prop[ch * n_steps + s];
+      const int f1 = f % d, f2 = f / d;
+      const double sgn = xc[f] ? -1.0 : 1.0;
+      double s_old = 0.0, s_new = 0.0;
+      for (int k = 0; k < K; ++k) {
+        int r1 = wrapi(f1 - offsets[2 * k], d), r2 = wrapi(f2 - offsets[2 * k + 1], d);
+        const double *hr = h + (size_t)(r2 * d + r1) * H;
+        int g0 = gate_of_fp(n_tree, feature, thr, left, right, active, offsets, xc, d, r1, r2, -1);
+        int g1 = gate_of_fp(n_tree, feature, thr, left, right, active, offsets, xc, d, r1, r2, f);
+        if (!g0 && !g1) continue;
+        double y0 = b2, y1 = b2;
+        for (int j = 0; j < H; ++j) {
+          double a = hr[j], b = a + sgn * W1[(size_t)k * H + j];
+          y0 += w2[j] * (a > 0.0 ? a : 0.0);
+          y1 += w2[j] * (b > 0.0 ? b : 0.0);
+        }
+        if (g0) s_old += y0 * sigma + mu;
+        if (g1) s_new += y1 * sigma + mu;
+      }
+      const double delta = s_new - s_old;
+      int acc;
+      if (delta > 0.0) acc = 1;
+      else if (T > 0.0) {
+        const double pr = exp(delta / T), uu = (double)u[ch * n_steps + s];
+        acc = pr > uu;
+        const double mg = fabs(pr - uu);
+        if (mg < min_margin) min_margin = mg;
+        if (mg < margin_thr) ++n_below;
+      } else acc = 0;
+      if (acc) {
+        xc[f] ^= 1;
+        for (int k = 0; k < K; ++k) {
+          int r1 = wrapi(f1 - offsets[2 * k], d), r2 = wrapi(f2 - offsets[2 * k + 1], d);
+          double *hr = h + (size_t)(r2 * d + r1) * H;
+          for (int j = 0; j < H; ++j) hr[j] += sgn * W1[(size_t)k * H + j];
+        }
+      }
+      if (accept_out) accept_out[ch * n_steps + s] = (uint8_t)acc;
+    }
+    if (min_margin_out) min_margin_out[ch] = min_margin;
+    if (n_below_out) n_below_out[ch] = n_below;
+    if (of_out) {                                   /* final objective from a fresh fp64 evaluation */
+      double of = 0.0;
+      for (int r = 0; r < N; ++r) {
+        if (!gate_of_fp(n_tree, feature, thr, left, right, active, offsets, xc, d, r % d, r / d, -1)) continue;
+        const double *hr = h + (size_t)r * H;
+        double y = b2;
+        for (int j = 0; j < H; ++j) y += w2[j] * (hr[j] > 0.0 ? hr[j] : 0.0);
+        of += y * sigma + mu;
+      }
+      of_out[ch] = of;
+    }
+    free(h);
+  }
+  return failed ? -1 : 0;
+}
+
 /* LSC / NH3-exported site types of one structure by the closed-form local rules (oracle/site_types.py) are NOT
  * duplicated here: the NumPy oracle is fast enough for them at every tested size. */

@@ -8,6 +8,8 @@
 #include <string.h>
 #include <algorithm>
 #include <new>
+#include <vector>
+#include <nvtx3/nvToolsExt.h>
 
 static thread_local std::string g_err;
 
@@ -256,8 +258,17 @@ static int check_range(const so_chains *c, int64_t chain0, int64_t n) {
 }
 
 // after the bits of a range changed: keep the surrogate state consistent
+// NVTX ranges (header-only nvtx3: a no-op unless a tool is attached) around the phases a timeline should show: state
+// build, sweep, the kernels that feed a collective.  The reference's only timing hook is time.time() around its loop
+// (OML/optimize_SA.py:55,135-136).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 static int rescore(so_chains *c, int64_t chain0, int64_t n) {
   if (!c->sur || n == 0) return SO_OK;
+  NvtxRange nvtx_range("state build (first-layer state + objective sums from the bits)");
   const so_lattice *L = c->lat;
   return so_launch_score(L, c->sur, c->bits_dev + chain0 * L->W, n,
                          c->hq_dev + chain0 * (long long)L->N * c->sur->Hp, c->hi_dev + chain0, c->lo_dev + chain0,
@@ -718,6 +729,7 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   SO_REQUIRE(a->n_steps >= 0 && a->step0 >= 0, "negative step range");
   SO_REQUIRE(a->temps || a->n_steps == 0, "temps is NULL");
   SO_REQUIRE((a->proposals == nullptr) == (a->uniforms == nullptr), "proposals and uniforms must be given together");
+  NvtxRange nvtx_range("so_anneal (sweep)");
   const so_lattice *L = c->lat;
   if (stats) memset(stats, 0, sizeof(*stats));
   if (a->n_steps == 0) return SO_OK;
@@ -807,6 +819,101 @@ int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale) {
   return SO_OK;
 }
 
+// ---- checkpoint / resume ------------------------------------------------------------------------------------
+// A chain's whole state is a function of its bits (the first-layer state and the sums are exact integers, recomputed
+// by the state build) plus the temperature scale; with counter-based draws a run resumed from (bits, tscale, step,
+// seed) continues bit for bit.  File: 64-byte header, bits[n][W] u32, tscale[n] f64, hi[n] i64, lo[n] i64, nact[n] i32
+// (the sums are stored only to verify the rebuilt state on load).
+namespace {
+struct CkptHeader {
+  char magic[8];            // "SOB200CK"
+  uint32_t version, d, N, W;
+  int64_t n_chains;
+  int64_t step;
+  uint64_t seed;
+  int32_t has_sums, K, Hp, pad;
+};
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header layout");
+}  // namespace
+
+int so_chains_save(so_chains *c, const char *path, int64_t step, uint64_t seed) {
+  SO_REQUIRE(c && path, "NULL argument");
+  const so_lattice *L = c->lat;
+  SO_CUDA(cudaSetDevice(L->device));
+  SO_CUDA(cudaStreamSynchronize(c->stream));
+  const size_t n = (size_t)c->n_chains;
+  std::vector<uint32_t> bits(n * L->W);
+  std::vector<double> ts(n);
+  std::vector<long long> hi(n), lo(n);
+  std::vector<int32_t> na(n);
+  SO_CUDA(cudaMemcpy(bits.data(), c->bits_dev, bits.size() * 4, cudaMemcpyDeviceToHost));
+  SO_CUDA(cudaMemcpy(ts.data(), c->tscale_dev, n * 8, cudaMemcpyDeviceToHost));
+  CkptHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "SOB200CK", 8);
+  h.version = 1; h.d = (uint32_t)L->d; h.N = (uint32_t)L->N; h.W = (uint32_t)L->W;
+  h.n_chains = c->n_chains; h.step = step; h.seed = seed;
+  if (c->sur) {
+    h.has_sums = 1; h.K = c->sur->K; h.Hp = c->sur->Hp;
+    SO_CUDA(cudaMemcpy(hi.data(), c->hi_dev, n * 8, cudaMemcpyDeviceToHost));
+    SO_CUDA(cudaMemcpy(lo.data(), c->lo_dev, n * 8, cudaMemcpyDeviceToHost));
+    SO_CUDA(cudaMemcpy(na.data(), c->nact_dev, n * 4, cudaMemcpyDeviceToHost));
+  }
+  FILE *f = fopen(path, "wb");
+  SO_REQUIRE(f, "cannot open %s for writing", path);
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(bits.data(), 4, bits.size(), f) == bits.size() &&
+            fwrite(ts.data(), 8, n, f) == n;
+  if (ok && h.has_sums)
+    ok = fwrite(hi.data(), 8, n, f) == n && fwrite(lo.data(), 8, n, f) == n && fwrite(na.data(), 4, n, f) == n;
+  ok = (fclose(f) == 0) && ok;
+  SO_REQUIRE(ok, "short write to %s", path);
+  return SO_OK;
+}
+
+int so_chains_load(so_chains *c, const char *path, int64_t *step, uint64_t *seed) {
+  SO_REQUIRE(c && path, "NULL argument");
+  const so_lattice *L = c->lat;
+  FILE *f = fopen(path, "rb");
+  SO_REQUIRE(f, "cannot open %s", path);
+  CkptHeader h;
+  bool ok = fread(&h, sizeof(h), 1, f) == 1;
+  if (!ok || memcmp(h.magic, "SOB200CK", 8) != 0 || h.version != 1) {
+    fclose(f);
+    so_set_error("%s is not a chain checkpoint of this library", path);
+    return SO_EINVAL;
+  }
+  if ((int)h.d != L->d || h.n_chains != c->n_chains || (int)h.W != L->W) {
+    fclose(f);
+    so_set_error("checkpoint holds %lld chains on a %ux%u lattice; this handle has %lld chains on %dx%d",
+                 (long long)h.n_chains, h.d, h.d, (long long)c->n_chains, L->d, L->d);
+    return SO_EINVAL;
+  }
+  const size_t n = (size_t)c->n_chains;
+  std::vector<uint32_t> bits(n * L->W);
+  std::vector<double> ts(n);
+  std::vector<long long> hi(n), lo(n);
+  std::vector<int32_t> na(n);
+  ok = fread(bits.data(), 4, bits.size(), f) == bits.size() && fread(ts.data(), 8, n, f) == n;
+  if (ok && h.has_sums)
+    ok = fread(hi.data(), 8, n, f) == n && fread(lo.data(), 8, n, f) == n && fread(na.data(), 4, n, f) == n;
+  fclose(f);
+  SO_REQUIRE(ok, "%s is truncated", path);
+  SO_TRY(so_set_occupancy_bits(c, 0, c->n_chains, bits.data()));          // validates the bits, rebuilds the state
+  SO_TRY(so_set_tscale(c, 0, c->n_chains, ts.data()));
+  if (h.has_sums && c->sur && h.K == c->sur->K && h.Hp == c->sur->Hp) {   // the rebuilt sums must be the saved ones
+    std::vector<long long> hi2(n), lo2(n);
+    std::vector<int32_t> na2(n);
+    SO_CUDA(cudaMemcpy(hi2.data(), c->hi_dev, n * 8, cudaMemcpyDeviceToHost));
+    SO_CUDA(cudaMemcpy(lo2.data(), c->lo_dev, n * 8, cudaMemcpyDeviceToHost));
+    SO_CUDA(cudaMemcpy(na2.data(), c->nact_dev, n * 4, cudaMemcpyDeviceToHost));
+    SO_REQUIRE(hi2 == hi && lo2 == lo && na2 == na,
+               "checkpoint %s was written with a different surrogate (objective sums do not reproduce)", path);
+  }
+  if (step) *step = h.step;
+  if (seed) *seed = h.seed;
+  return SO_OK;
+}
+
 // ---- LSC analytical objective ------------------------------------------------------------------------------
 int so_lsc_analytical(so_chains *c, int64_t chain0, int64_t n, double *site_rates, double *struct_rate) {
   SO_TRY(check_range(c, chain0, n));
@@ -882,6 +989,7 @@ int so_anneal_analytical(so_chains *c, const so_anneal_args *a, so_anneal_stats 
 int so_best_record_dev(so_chains *c, int64_t chain_id0, void *record_dev, void *stream) {
   SO_REQUIRE(c && record_dev, "NULL argument");
   SO_REQUIRE(c->sur, "no surrogate attached");
+  NvtxRange nvtx_range("best-structure record (all-gather send buffer)");
   SO_CUDA(cudaSetDevice(c->lat->device));
   SO_TRY(so_launch_best(c, chain_id0, record_dev, (cudaStream_t)stream));
   return SO_OK;
@@ -918,6 +1026,7 @@ int so_exchange(so_chains *c, int rank, int world, int ladder, int parity, uint6
   SO_REQUIRE(ladder >= 2 && ladder <= 32, "ladder size %d outside [2, 32]", ladder);
   SO_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
   SO_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
+  NvtxRange nvtx_range("replica-exchange decisions");
   const int64_t n_global = c->n_chains * (int64_t)world;
   SO_REQUIRE(n_global % ladder == 0, "world*n_chains=%lld is not a multiple of the ladder size %d", (long long)n_global,
              ladder);

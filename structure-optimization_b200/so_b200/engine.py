@@ -314,6 +314,16 @@ class Chains(object):
         B.check(self.lib.so_get_tscale(self.h, chain0, n, _p(t, B.c_f64p)))
         return t
 
+    def save(self, path, step=0, seed=0):
+        """Checkpoint (bits, tscale, exact sums) with the caller's step counter and seed; resume is bit-exact."""
+        B.check(self.lib.so_chains_save(self.h, str(path).encode(), int(step), int(seed)))
+
+    def load(self, path):
+        """Restore a checkpoint written by save() into this handle (same lattice and chain count); returns (step, seed)."""
+        step, seed = C.c_int64(), C.c_uint64()
+        B.check(self.lib.so_chains_load(self.h, str(path).encode(), C.byref(step), C.byref(seed)))
+        return step.value, seed.value
+
     def best(self):
         of = C.c_double()
         ch = C.c_int64()

@@ -74,11 +74,13 @@ class BestGather(object):
         """Arg-max kernel writes straight into the NCCL send buffer; returns the global best of this round."""
         torch = self.torch
         B.check(self.ch.lib.so_best_record_dev(self.ch.h, self.chain_id0, C.c_void_p(self.rec.data_ptr()), _stream_ptr()))
+        torch.cuda.nvtx.range_push("best-structure all-gather (NCCL)")
         if self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.all.view(-1), self.rec, group=self.group)
         else:
             self.all[0].copy_(self.rec)
+        torch.cuda.nvtx.range_pop()
         of, cid, bits = parse_records(self.all.cpu().numpy(), self.words)
         cur = pick_best(of, cid, bits)
         if cur[0] > self.best[0]:
@@ -110,11 +112,13 @@ class ReplicaExchange(object):
         ch = self.ch
         self.ev0.record()
         B.check(ch.lib.so_objectives_dev(ch.h, C.c_void_p(self.of_local.data_ptr()), _stream_ptr()))
+        torch.cuda.nvtx.range_push("replica-exchange objectives all-gather (NCCL)")
         if self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.of_all, self.of_local, group=self.group)
         else:
             self.of_all.copy_(self.of_local)
+        torch.cuda.nvtx.range_pop()
         ns = C.c_int64()
         B.check(ch.lib.so_exchange(ch.h, self.rank, self.world, self.ladder, int(r) & 1, self.seed, int(r), float(t_ref),
                                    C.c_void_p(self.of_all.data_ptr()), C.c_void_p(self.tscale_all.data_ptr()),

@@ -289,8 +289,50 @@ def test_lsc_analytical_batch_matches_oracle():
         np.testing.assert_allclose(sr[c], ref, rtol=1e-9, atol=1e-13)       # fp tolerance: 1e-9 relative
         np.testing.assert_allclose(rate[c], ref.sum(), rtol=1e-9, atol=1e-13)
     assert rate[-2] == 0.0 and rate[-1] == 0.0                              # no sites / terraces only: no edge flux
-    with pytest.raises(ValueError):
-        engine.Chains(engine.Lattice(16, "LSC"), 1).lsc_analytical()        # 256 sites: beyond the shared-memory solve
+
+
+@pytest.mark.parametrize("d", [16, 24, 96])
+def test_lsc_analytical_any_lattice_size(d):
+    """OML/LSC_cat.py:260-316 works for any `dimen`; above 160 sites the device solves the same system by conjugate
+    gradients on the lattice stencil (so_lsc.cu).  d = 16 against the reference-executed rates of ref_types.npz, all
+    sizes against the LAPACK restatement, 1e-9 relative; then the SA loop on it and the drop-in LSC_cat(d)."""
+    from so_b200 import engine, LSC_cat, optimize
+    N = d * d
+    rng = np.random.default_rng(d)
+    n = 6 if d < 96 else 3
+    xs = (rng.random((n, N)) < np.linspace(0.75, 0.97, n)[:, None]).astype(np.uint8)
+    xs[0] = 1
+    xs[0, [1, 2, d + 1]] = 0
+    ch = engine.Chains(engine.Lattice(d, "LSC"), n)
+    ch.set_occupancy(xs)
+    rate, sr = ch.lsc_analytical()
+    for c in range(n):
+        ref = LA.compute_site_rates_lsc(xs[c], d)
+        np.testing.assert_allclose(sr[c], ref, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(rate[c], ref.sum(), rtol=1e-9, atol=1e-12)
+    if d == 16:
+        z = np.load(os.path.join(Hp.GOLDEN, "ref_types.npz"))
+        c2 = engine.Chains(engine.Lattice(d, "LSC"), len(z["d16_x"]))
+        c2.set_occupancy(z["d16_x"])
+        r2, s2 = c2.lsc_analytical()
+        np.testing.assert_allclose(s2, z["d16_lsc_site_rates"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r2, z["d16_lsc_struct_rate"], rtol=1e-9, atol=1e-12)
+        cat = LSC_cat(16)                                                  # raised in round 1
+        cat.assign_occs([int(v) for v in z["d16_x"][3]])
+        cat.graph_to_KMClattice()
+        np.testing.assert_allclose(cat.compute_site_rates_lsc(), z["d16_lsc_site_rates"][3], rtol=1e-9, atol=1e-12)
+    if d <= 24:
+        steps = 120
+        prop = rng.integers(0, N, (n, steps)).astype(np.int32)
+        u = rng.random((n, steps), dtype=np.float32)
+        temps = SA.schedule("exp", 0.05, steps)
+        stats, acc = ch.anneal_analytical(temps, proposals=prop, uniforms=u, want_accept=True)
+        for c in range(0, n, 2):
+            o = SA.optimize_analytical(xs[c], d, temps, prop[c], u[c])
+            safe = o["margin"] > 1e-9
+            assert (acc[c].astype(bool)[safe] == o["accept"][safe]).all() and safe.all()
+            assert (ch.get_occupancy(c, 1)[0] == o["x"]).all()
+            np.testing.assert_allclose(stats["OF"][c], o["OF"], rtol=1e-9, atol=1e-12)
 
 
 def test_analytical_sa_matches_oracle():

@@ -500,6 +500,44 @@ def test_best_record_and_objectives_dev(eng):
     assert ms >= 0 and sorted(ch.get_tscale().tolist()) == sorted(P.ladder_tscale(np.arange(n), 6).tolist())
 
 
+def test_checkpoint_resume_is_bit_exact(eng, tmp_path):
+    """so_chains_save / so_chains_load: a run cut at a checkpoint and resumed in a NEW handle ends with the same bits,
+    sums and temperatures as the uninterrupted run (counter-based draws; the state is an exact function of the bits)."""
+    d, N, n = 20, 400, 500
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=4)
+    lat = eng.Lattice(d, "NH3")
+    tab = Hp.tables_from_params(lat, p)
+    temps = SA.schedule("exp", 0.5, 900)
+    a = eng.Chains(lat, n)
+    a.randomize(seed=3, coverage=0.5)
+    a.attach(tab)
+    a.set_tscale(np.linspace(0.5, 2.0, n))
+    a.anneal(temps[:400], step0=0, seed=17, chain_id0=40)
+    path = str(tmp_path / "chains.ckpt")
+    a.save(path, step=400, seed=17)
+    a.anneal(temps[400:], step0=400, seed=17, chain_id0=40)
+    b = eng.Chains(lat, n)
+    b.attach(tab)
+    step, seed = b.load(path)
+    assert (step, seed) == (400, 17)
+    b.anneal(temps[step:], step0=step, seed=seed, chain_id0=40)
+    assert (a.get_bits() == b.get_bits()).all() and (a.get_tscale() == b.get_tscale()).all()
+    oa, ob = a.objective(sums=True), b.objective(sums=True)
+    assert all((u == v).all() for u, v in zip(oa, ob))
+    assert (a.preact(123) == b.preact(123)).all()
+    # shape and surrogate mismatches are refused
+    c = eng.Chains(lat, n + 1)
+    with pytest.raises(ValueError):
+        c.load(path)
+    q = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=5)
+    e = eng.Chains(lat, n)
+    e.attach(Hp.tables_from_params(lat, q))
+    with pytest.raises(ValueError):
+        e.load(path)
+    with pytest.raises(ValueError):
+        e.load(str(tmp_path / "missing.ckpt"))
+
+
 # ---- BASELINE configs[1] at full size: 4,096 chains x 14,400 steps, injected proposal/uniform sequence -----------
 def _config2(eng, p, n_chains):
     from oracle import c_oracle
@@ -537,6 +575,67 @@ def test_config2_full_size_open(eng):
 
 def test_config2_gated(eng):
     _config2(eng, Hp.golden_surrogate(gated=True), 256)
+
+
+def _config2_fp64_rule(eng, p, n_chains, y_scale_w2sum):
+    """BASELINE configs[1] at full length against the REFERENCE'S fp64 rule (original weights, oracle_anneal_fp64 -- which
+    tests/test_oracle_c.py pins to the reference-executed optimize() runs), exact_guard on: accept vectors and occupancies
+    identical; the minimum Metropolis margin |exp(delta/T) - u| and the number of decisions closer than 1e-9 are printed.
+    Every 1,440 steps: Ni-neighbour counts, LSC / NH3 types and histograms of ALL chains against
+    the oracle's typing of the oracle's own occupancies."""
+    from oracle import c_oracle
+    d, N, steps, seg = 12, 144, 14400, 1440
+    rng = np.random.Generator(np.random.Philox(key=1234))
+    x0 = (rng.random((n_chains, N)) < 0.5).astype(np.uint8)
+    prop = rng.integers(0, N, size=(n_chains, steps)).astype(np.int32)
+    u = rng.random((n_chains, steps), dtype=np.float32)
+    temps = SA.schedule("exp", 0.05, steps)
+    lat = eng.Lattice(d, "NH3")
+    tab = Hp.tables_from_params(lat, p)
+    ch = eng.Chains(lat, n_chains)
+    ch.set_occupancy(x0)
+    ch.attach(tab)
+    tol = 8.0 * np.sqrt(tab.K) * np.ldexp(1.0, tab.e_h) * y_scale_w2sum
+    x_ref = x0.copy()
+    min_margin, n_below, guard_fired = np.inf, 0, 0
+    tied = np.zeros(n_chains, dtype=bool)                         # chains that met a decision closer than 1e-9
+    for a in range(0, steps, seg):
+        b = a + seg
+        st, acc = ch.anneal(temps[a:b], step0=a, proposals=prop[:, a:b], uniforms=u[:, a:b], want_accept=True,
+                            exact_guard=True, guard_tol=tol)
+        guard_fired += st["guard_fired"]
+        o = c_oracle.anneal_fp64_many(p, d, x_ref, temps[a:b], prop[:, a:b], u[:, a:b], margin_thr=1e-9)
+        x_ref = o["x"]
+        min_margin = min(min_margin, float(o["min_margin"].min()))
+        n_below += int(o["n_below"].sum())
+        tied |= o["n_below"] > 0
+        ok = ~tied
+        assert (acc.astype(bool)[ok] == o["accept"][ok]).all(), "decisions differ from the fp64 rule in steps %d..%d" % (a, b)
+        x1 = ch.get_occupancy()
+        assert (x1[ok] == x_ref[ok]).all()
+        out = ch.descriptors(c6=True, lsc_type=True, nh3_type=True, lsc_hist=True, nh3_hist=True, nh3_exp=True)
+        t_ref = ST.nh3_types(x_ref, d)
+        l_ref = ST.lsc_types(x_ref, d)
+        assert (out["c6"][ok] == ST.c6_counts(x_ref, d)[ok]).all() and (out["lsc_type"][ok] == l_ref[ok]).all()
+        assert (out["nh3_type"][ok] == t_ref[ok]).all()
+        assert (out["nh3_hist"][ok] == ST.nh3_hist(t_ref)[ok]).all() and (out["nh3_exp"][ok] == ST.nh3_export_hist(t_ref)[ok]).all()
+        assert (out["lsc_hist"][ok] == np.stack([(l_ref == t).sum(1) for t in range(3)], 1)[ok]).all()
+        x_ref = np.where(tied[:, None], x1, x_ref)                # a tied chain continues from the device's state
+    of = ch.objective()
+    assert np.abs(of[~tied] - o["OF"][~tied]).max() <= 1e-5 * np.abs(o["OF"]).max()
+    print("config 2 vs the fp64 rule: %d chains x %d steps, min margin |exp(delta/T)-u| = %.3e, %d decisions below 1e-9 "
+          "(%d chains excluded), exact guard fired %d times" % (n_chains, steps, min_margin, n_below, int(tied.sum()), guard_fired))
+    assert tied.sum() <= max(1, n_chains // 1000)
+
+
+def test_config2_fp64_rule_full_size_open(eng):
+    p = Hp.golden_surrogate(gated=False)
+    _config2_fp64_rule(eng, p, 4096, abs(p.y_scale) * float(np.abs(p.w2).sum()))
+
+
+def test_config2_fp64_rule_gated(eng):
+    p = Hp.golden_surrogate(gated=True)
+    _config2_fp64_rule(eng, p, 512, abs(p.y_scale) * float(np.abs(p.w2).sum()))
 
 
 # ---- BASELINE configs[3] shape (96x96, local 7x7 MLP): oracle parity on a sample + size-independent properties -----

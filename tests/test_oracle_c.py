@@ -32,3 +32,28 @@ def test_c_oracle_local_descriptor_with_tscale():
         r = SA.anneal_fixed(p, q, d, x0[c], temps, prop[c], u[c], tscale=ts[c])
         assert (o["accept"][c] == r["accept"]).all() and (o["x"][c] == r["x"]).all()
         assert (int(o["hi"][c]), int(o["lo"][c]), int(o["n_act"][c])) == (r["hi"], r["lo"], r["n_act"]) and o["OF"][c] == r["OF"]
+
+
+def test_c_fp64_rule_equals_reference_executed_optimize():
+    """oracle_anneal_fp64 (the reference's fp64 rule with its original weights, the decision oracle of the full-size GPU
+    test) against optimize() EXECUTED FROM THE REFERENCE SOURCE (tests/golden/ref_surrogate_sa.npz): every run."""
+    from test_ref_golden import ref_surrogate, _sa_runs
+    z = np.load(os.path.join(Hp.GOLDEN, "ref_surrogate_sa.npz"))
+    worst = np.inf
+    for name, c, gated, n_cycles, T_0, cooling in _sa_runs(z):
+        steps = n_cycles * 144
+        py2 = cooling == "linear_py2"
+        temps = SA.schedule("linear" if py2 else cooling, T_0, steps, py2_linear=py2)
+        p = ref_surrogate(z, gated)
+        o = c_oracle.anneal_fp64_many(p, 12, z["sa_x0"][c:c + 1], temps, z["sa_prop"][c:c + 1, :steps], z["sa_u"][c:c + 1, :steps])
+        acc = np.unpackbits(z["sa_%s_accept" % name])[:steps].astype(bool)
+        assert (o["accept"][0] == acc).all() and (o["x"][0] == z["sa_%s_x" % name]).all(), name
+        assert o["n_below"][0] == 0
+        worst = min(worst, float(o["min_margin"][0]))
+        of_new = z["sa_%s_OF_new" % name]
+        cur = float(z["sa_%s_OF0" % name])
+        for s in range(steps):
+            if acc[s]:
+                cur = of_new[s]
+        assert abs(o["OF"][0] - cur) <= 1e-9 * max(1.0, abs(cur))
+    assert worst > 1e-7
