@@ -232,29 +232,79 @@ def pt_self_check(pt, ch, tscale_initial, rounds_done, rank, world, dist, n_samp
             "swap_rounds_run": int(rounds_done)}
 
 
-def accept_sweeps(ch, a, N, chain_id0, peak, targets=(0.5, 0.2, 0.05)):
-    """The hot kernel where flips ARE accepted: one full sweep of every chain at a CONSTANT temperature chosen (by
-    bisection on short launches) so that the accept fraction is about each target; same shape as the headline.
-    Returns [{target, T, accept_fraction, ms, value, bytes_per_flip, achieved GB/s, frac}]."""
+def other_configs():
+    """BASELINE configs[1] and configs[2] next to the headline (untimed tail of the default N=1 run; they are parity-test
+    cases, the numbers are for the record): 4,096 chains on the reference's 12x12 lattice with the full 144-column
+    descriptor and a tree gate (one sweep-equivalent of 14,400 steps, Philox draws), and batch scoring of 2^20 random
+    structures (host bits in, host rates + LSC / NH3-exported histograms out)."""
+    import torch
+    from so_b200 import engine
+    out = {}
+    d, N = 12, 144
+    lat = engine.Lattice(d, "NH3", device=torch.cuda.current_device())
+    off = engine.full_offsets(d)
+    W1, b1, w2, b2 = glorot_mlp(off, H, 0)
+    rng = np.random.default_rng(0)
+    depth = 8                                              # synthetic depth-8 gate on the 144 columns
+
+    def node(level, t):
+        i = len(t["feature"])
+        for k, v in (("feature", -2), ("thr", 0.0), ("left", -1), ("right", -1), ("active", int(rng.random() < 0.6))):
+            t[k].append(v)
+        if level < depth:
+            t["feature"][i], t["thr"][i] = int(rng.integers(0, N)), 0.5
+            t["left"][i] = node(level + 1, t)
+            t["right"][i] = node(level + 1, t)
+        return i
+    t = dict(feature=[], thr=[], left=[], right=[], active=[])
+    node(0, t)
+    tree = dict(feature=np.array(t["feature"], np.int32), thr=np.array(t["thr"]), left=np.array(t["left"], np.int32),
+                right=np.array(t["right"], np.int32), active=np.array(t["active"], np.uint8))
+    for name, tr in (("gated", tree), ("gate_off", None)):
+        tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=tr)
+        ch = engine.Chains(lat, 4096)
+        ch.randomize(seed=1234, coverage=0.5)
+        ch.attach(tab)
+        temps = exp_schedule(T0, 2 * 14400)
+        ch.anneal(temps[:14400], step0=0, seed=5)
+        st = ch.anneal(temps[14400:], step0=14400, seed=5)
+        out["configs[1] 12x12, 4096 chains x 14400 steps, full descriptor, " + name] = {
+            "value": st["flips"] / (st["kernel_ms"] * 1e-3), "unit": UNIT, "kernel": st["kernel"], "ms": st["kernel_ms"],
+            "accept_fraction": st["accepted"] / st["flips"]}
+        ch.close()
+    n = 1 << 20
+    cov = rng.random((n, 1))
+    bits = engine.pack_bits((rng.random((n, N)) < cov).astype(np.uint8))
+    tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    bits_p = pin(bits.shape, torch.int32).view(np.uint32)
+    bits_p[:] = bits
+    res = (pin((n,), torch.float64), pin((n, 3), torch.int32), pin((n, 8), torch.int32))
+    tab.score_batch(bits_p, out=res)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        tab.score_batch(bits_p, out=res)
+    dt = (time.perf_counter() - t0) / 3
+    out["configs[2] batch scoring, 2^20 structures, 12x12 (host in, host out)"] = {
+        "value": n / dt, "unit": "structures/s", "ms": 1e3 * dt, "h2d_bytes": int(bits.nbytes),
+        "d2h_bytes": int(sum(r.nbytes for r in res))}
+    return out
+
+
+# constant temperatures at which the bench workload (96x96, 7x7-window MLP, Glorot seed 0) accepts about 0.5 / 0.2 / 0.05
+# of its proposals in equilibrium: profiles/r02_accept_calibration.txt (scripts/calibrate_accept.py)
+ACCEPT_SWEEP_TEMPS = ((0.5, 1.55), (0.2, 0.87), (0.05, 0.565))
+
+
+def accept_sweeps(ch, a, N, chain_id0, peak):
+    """The hot kernel where flips ARE accepted: chains re-randomised, then for each calibrated constant temperature
+    (descending) two sweeps of every chain to equilibrate and one measured sweep, same shape as the headline (which
+    anneals from T0 = 0.05 and is frozen after its warm-up).  Returns [{target, T, accept_fraction (measured), ms, value, bytes_per_flip, achieved GB/s, frac}]."""
     out = []
-    probe = max(32, min(N, 256))
     step0 = 10 ** 9                                  # Philox counters far away from the timed region
-    lo_T, hi_T = 1e-4, 1e3
-    for tgt in targets:
-        lo, hi = lo_T, hi_T
-        T = np.sqrt(lo * hi)
-        for it in range(14):
-            T = np.sqrt(lo * hi)
-            st = ch.anneal(np.full(probe, T), step0=step0, seed=a.seed + 1, chain_id0=chain_id0)
-            step0 += probe
-            frac = st["accepted"] / max(st["flips"], 1)
-            if abs(frac - tgt) <= 0.02 * max(tgt, 0.1):
-                break
-            if frac > tgt:
-                hi = T
-            else:
-                lo = T
-        for rep in range(2):                          # one sweep to equilibrate at T, one measured
+    ch.randomize(seed=4321 + chain_id0, coverage=0.5)     # the headline left the chains frozen: restart hot, cool stepwise
+    for tgt, T in ACCEPT_SWEEP_TEMPS:
+        for rep in range(3):                          # two sweeps to equilibrate at T, the third is the measured one
             st = ch.anneal(np.full(N, T), step0=step0, seed=a.seed + 1, chain_id0=chain_id0)
             step0 += N
         af = st["accepted"] / max(st["flips"], 1)
@@ -263,7 +313,6 @@ def accept_sweeps(ch, a, N, chain_id0, peak, targets=(0.5, 0.2, 0.05)):
         out.append({"target": tgt, "T": float(T), "accept_fraction": af, "ms": st["kernel_ms"],
                     "value": st["flips"] / (st["kernel_ms"] * 1e-3), "bytes_per_flip": b_alg, "achieved": ach,
                     "frac": ach / peak, "kernel": st["kernel"]})
-        hi_T = T                                      # next (smaller) target: colder
     return out
 
 
@@ -399,11 +448,16 @@ def run_gpu(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kern_s = kern_ms * 1e-3
     achieved = (flips_all / world) * b_alg / kern_s / 1e9 if world == 1 else float(flips) * b_alg / kern_s / 1e9
+    # DRAM bytes of one launch from the committed ncu capture of THIS command at THIS shape (profiles/); null otherwise
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("sa_window_kernel")
+            tj = json.load(open(tpath))
+            sh = tj.get("shape", {})
+            if (sh.get("lattice") == "%dx%d" % (d, d) and sh.get("chains") == n_local and sh.get("steps_per_launch") == N
+                    and str(kernel_name) in str(sh.get("kernel"))):
+                traffic = tj.get("sa_window_kernel")
         except Exception:
             traffic = None
     line = {
@@ -427,6 +481,9 @@ def run_gpu(a):
         line["pt_self_check"] = pt_check
     if world == 1 and pt is None and a.accept_sweep:
         line["accept_sweep"] = accept_sweeps(ch, a, N, chain_id0, peak)
+    if world == 1 and pt is None and a.other_configs:
+        ch.close()
+        line["other_configs"] = other_configs()
     if world == 1 and a.cpu_flips > 0:
         cores = os.cpu_count() or 1
         v, wall = cpu_reference_rate(d, a.cpu_flips, cores, total_sweeps * N)
@@ -553,6 +610,7 @@ def main():
     ap.add_argument("--gather-every", type=int, default=0, help="best-structure all-gather period in sweeps (0 = 10 with PT, 1 without)")
     ap.add_argument("--ladder", type=int, default=8, help="parallel-tempering ladder size")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--other-configs", type=int, default=1, help="1: also record BASELINE configs[1] and configs[2] numbers")
     ap.add_argument("--accept-sweep", type=int, default=1, help="1: also time one sweep at accept fractions 0.5/0.2/0.05")
     ap.add_argument("--cpu-flips", type=int, default=3000, help="Metropolis steps per core for the CPU baseline (0 = skip)")
     ap.add_argument("--ref-flips", type=int, default=1000, help="Metropolis steps per core per bench step, --impl reference")

@@ -58,6 +58,11 @@ int so_get_occupancy_bits(so_chains *c, int64_t chain0, int64_t n, uint32_t *bit
 /* randomize (OML/dynamic_cat.py:62-84) on device: Bernoulli(p) bits per site, p = coverage, or p ~ U(0,1)
  * per chain when coverage < 0 (the reference's coverage=None); Philox stream `seed`.                      */
 int so_randomize(so_chains *c, uint64_t seed, double coverage);
+/* seeded island structures, the initial-population recipe of drivers/generate_init_structures.py:26-116, on the device:
+ * chain chain0+k becomes structure index[k] of n_strucs (np.random.seed(index[k]); int(3 + 15*i/(n_strucs+1)) 19-site
+ * hexagonal islands around sites drawn without replacement; then n_mutate (16 upstream) sites toggled) -- NumPy's
+ * legacy MT19937 / choice(replace=False) stream restated bit for bit.                                        */
+int so_island_structures(so_chains *c, int64_t chain0, int64_t n, const int32_t *index, int n_strucs, int n_mutate);
 /* flip_atom (OML/dynamic_cat.py:172-185) for a list of (chain, variable-site index) pairs; keeps the
  * surrogate state (if attached) consistent.                                                             */
 int so_flip(so_chains *c, int64_t n, const int64_t *chains, const int32_t *sites);

@@ -353,6 +353,29 @@ int so_randomize(so_chains *c, uint64_t seed, double coverage) {
   return SO_OK;
 }
 
+int so_island_structures(so_chains *c, int64_t chain0, int64_t n, const int32_t *index, int n_strucs, int n_mutate) {
+  SO_TRY(check_range(c, chain0, n));
+  SO_REQUIRE(index || n == 0, "index is NULL");
+  SO_REQUIRE(n_strucs >= 1 && n_mutate >= 0, "n_strucs must be positive and n_mutate non-negative");
+  for (int64_t k = 0; k < n; ++k) SO_REQUIRE(index[k] >= 0, "structure index %lld is negative (np.random.seed needs >= 0)", (long long)k);
+  if (n == 0) return SO_OK;
+  const so_lattice *L = c->lat;
+  SO_CUDA(cudaSetDevice(L->device));
+  const int64_t slab = std::max<int64_t>(1, (1LL << 30) / ((int64_t)L->N * 4));      // <= 1 GiB of permutation scratch
+  DevBuf d_idx, d_perm;
+  SO_TRY(d_idx.alloc((size_t)n * 4));
+  SO_TRY(d_perm.alloc((size_t)std::min(slab, n) * L->N * 4));
+  SO_CUDA(cudaMemcpyAsync(d_idx.p, index, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  for (int64_t k0 = 0; k0 < n; k0 += slab) {
+    const int64_t nk = std::min(slab, n - k0);
+    SO_TRY(so_launch_islands(c->bits_dev + (chain0 + k0) * L->W, nk, L->d, L->N, L->W, d_idx.as<int32_t>() + k0, n_strucs,
+                             n_mutate, d_perm.as<int32_t>(), c->stream));
+  }
+  SO_TRY(rescore(c, chain0, n));
+  SO_CUDA(cudaStreamSynchronize(c->stream));
+  return SO_OK;
+}
+
 int so_flip(so_chains *c, int64_t n, const int64_t *chains, const int32_t *sites) {
   SO_REQUIRE(c, "chains handle is NULL");
   SO_REQUIRE(n >= 0 && (n == 0 || (chains && sites)), "bad flip list");
@@ -391,7 +414,9 @@ int so_descriptors(so_chains *c, int64_t chain0, int64_t n, uint8_t *c6, uint8_t
   const so_lattice *L = c->lat;
   SO_CUDA(cudaSetDevice(L->device));
   const int N = L->N;
-  const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(65535, (64LL << 20) / (5LL * N)));
+  // staging slab: 256 MB of the outputs actually requested (histograms alone are 124 B per structure: one launch)
+  const int64_t out_bytes = (c6 ? N : 0) + (lsc_type ? N : 0) + (nh3_type ? 5LL * N : 0) + 124;
+  const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(1LL << 22, (256LL << 20) / out_bytes));
   DevBuf b_c6, b_lsc, b_nh3, b_lh, b_nh, b_ne;
   int64_t cap = std::min(slab, std::max<int64_t>(n, 1));
   if (c6) SO_TRY(b_c6.alloc((size_t)cap * N));

@@ -71,6 +71,82 @@ __global__ void randomize_kernel(uint32_t *bits, long long n, int N, int W, unsi
   bits[t] = word;
 }
 
+// ---- seeded island structures (drivers/generate_init_structures.py:26-116) ---------------------------------------------
+// Structure i of n_strucs: np.random.seed(i); n_tops = int(3 + 15*i/(n_strucs+1)) sites drawn with
+// np.random.choice(range(N), size=n_tops, replace=False), a 19-site hexagonal island of Ni around each; then n_mutate
+// sites drawn the same way are toggled.  NumPy's legacy stream is restated exactly: MT19937 seeded by init_genrand,
+// choice(replace=False) = the first `size` entries of permutation(N) = Fisher-Yates from the top with
+// random_interval (smallest bit mask >= i, 32-bit draws, rejection).  One thread per structure; the 624-word generator
+// state lives in local memory, the permutation in a global scratch row.
+struct Mt19937 {
+  uint32_t mt[624];
+  int pos;
+  __device__ void seed(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    pos = 624;
+  }
+  __device__ uint32_t next() {
+    if (pos >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1 == 624 ? 0 : k + 1] & 0x7fffffffu);
+        mt[k] = mt[k + 397 >= 624 ? k + 397 - 624 : k + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      pos = 0;
+    }
+    uint32_t y = mt[pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  __device__ uint32_t interval(uint32_t mx) {          // numpy random_interval, max <= 0xffffffff
+    if (mx == 0) return 0;
+    uint32_t mask = mx;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    while ((v = next() & mask) > mx) {}
+    return v;
+  }
+  __device__ void permutation(int32_t *a, int n) {     // RandomState.permutation(n): arange + legacy shuffle
+    for (int i = 0; i < n; ++i) a[i] = i;
+    for (int i = n - 1; i >= 1; --i) {
+      int j = (int)interval((uint32_t)i);
+      int32_t t = a[i]; a[i] = a[j]; a[j] = t;
+    }
+  }
+};
+
+__device__ __constant__ int8_t island_o1[19] = {-2, -1, 0, -2, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 2, 0, 1, 2};
+__device__ __constant__ int8_t island_o2[19] = {2, 2, 2, 1, 1, 1, 1, 0, 0, 0, 0, 0, -1, -1, -1, -1, -2, -2, -2};
+
+__global__ void island_kernel(uint32_t *bits, long long n, int d, int N, int W, const int32_t *index, int n_strucs,
+                              int n_mutate, int32_t *scratch) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t *x = bits + t * W;
+  int32_t *perm = scratch + t * N;
+  for (int w = 0; w < W; ++w) x[w] = 0;
+  const int i = index[t];
+  Mt19937 g;
+  g.seed((uint32_t)i);
+  const int n_tops = (int)(3.0 + 15.0 * (double)i / (double)(n_strucs + 1));
+  g.permutation(perm, N);
+  for (int k = 0; k < n_tops && k < N; ++k) {
+    const int top = perm[k], t2 = top / d, t1 = top - t2 * d;
+    for (int q = 0; q < 19; ++q) {
+      int v = wrap(t2 + island_o2[q], d) * d + wrap(t1 + island_o1[q], d);
+      x[v >> 5] |= 1u << (v & 31);
+    }
+  }
+  g.permutation(perm, N);
+  for (int k = 0; k < n_mutate && k < N; ++k) {
+    const int v = perm[k];
+    x[v >> 5] ^= 1u << (v & 31);
+  }
+}
+
 // ---- closed-form typing rules -----------------------------------------------------------------------
 struct L3Info {
   int x, c6, adj;   // occupancy, Ni neighbours, "two ring-adjacent vacancies"
@@ -516,6 +592,13 @@ int so_launch_randomize(uint32_t *bits_dev, int64_t n, int N, int W, uint64_t se
   long long total = n * W;
   if (total == 0) return SO_OK;
   randomize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bits_dev, n, N, W, seed, coverage);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_islands(uint32_t *bits_dev, int64_t n, int d, int N, int W, const int32_t *index_dev, int n_strucs, int n_mutate,
+                      int32_t *scratch_dev, cudaStream_t st) {
+  if (n == 0) return SO_OK;
+  island_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(bits_dev, n, d, N, W, index_dev, n_strucs, n_mutate, scratch_dev);
   SO_CUDA(cudaGetLastError());
   return SO_OK;
 }

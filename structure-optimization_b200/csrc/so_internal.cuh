@@ -145,6 +145,8 @@ int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_
 enum { SO_K_NONE = 0, SO_K_TEAM = 1, SO_K_RESIDENT = 2, SO_K_GATE_INDEX = 3, SO_K_WINDOW = 4, SO_K_FLAT = 5, SO_K_GATED = 6,
        SO_K_ANALYTICAL = 7 };
 int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int *kernel_id);
+int so_launch_islands(uint32_t *bits_dev, int64_t n, int d, int N, int W, const int32_t *index_dev, int n_strucs, int n_mutate,
+                      int32_t *scratch_dev, cudaStream_t st);
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);

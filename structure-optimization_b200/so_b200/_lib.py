@@ -56,6 +56,7 @@ PROTOTYPES = {
     "so_set_occupancy_bits": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_u32p]),
     "so_get_occupancy_bits": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_u32p]),
     "so_randomize": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double]),
+    "so_island_structures": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_i32p, C.c_int, C.c_int]),
     "so_flip": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_i32p]),
     "so_descriptors": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_u8p, c_u8p, c_u8p, c_i32p, c_i32p, c_i32p]),
     "so_flip_delta": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_i32p, c_i32p, c_i32p]),

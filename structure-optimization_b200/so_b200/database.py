@@ -48,6 +48,19 @@ def read_database(fldr_list):
     return [np.vstack(sym_list), np.vstack(site_rate_list)]
 
 
+def make_random_structures_device(lattice, indices, n_strucs, n_mutate=16):
+    """The same recipe for many structures at once, generated on the device (so_island_structures): returns the
+    occupancies [len(indices), N] uint8; bit-equal to make_random_structure(i, n_strucs, ...) for every i."""
+    from . import engine
+    indices = np.asarray(indices, dtype=np.int32).reshape(-1)
+    ch = engine.Chains(lattice, len(indices))
+    try:
+        ch.island_structures(indices, n_strucs=n_strucs, n_mutate=n_mutate)
+        return ch.get_occupancy()
+    finally:
+        ch.close()
+
+
 def make_random_structure(i, n_strucs, cat, fldr_name=None):
     """Seeded island structure number i of n_strucs: n_tops 19-site hexagonal islands, then 16 random mutations."""
     np.random.seed(i)

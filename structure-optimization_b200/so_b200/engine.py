@@ -190,6 +190,13 @@ class Chains(object):
     def randomize(self, seed, coverage=None):
         B.check(self.lib.so_randomize(self.h, int(seed), -1.0 if coverage is None else float(coverage)))
 
+    def island_structures(self, index, n_strucs=48, n_mutate=16, chain0=0):
+        """Chains chain0.. become the seeded island structures index[k] of n_strucs
+        (drivers/generate_init_structures.py:26-116, same NumPy legacy stream), generated on the device."""
+        index = np.ascontiguousarray(index, dtype=np.int32).reshape(-1)
+        B.check(self.lib.so_island_structures(self.h, int(chain0), len(index), _p(index, B.c_i32p), int(n_strucs),
+                                              int(n_mutate)))
+
     def flip(self, chains, sites):
         chains = np.ascontiguousarray(chains, dtype=np.int64).reshape(-1)
         sites = np.ascontiguousarray(sites, dtype=np.int32).reshape(-1)

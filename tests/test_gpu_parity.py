@@ -687,7 +687,7 @@ def test_config4_lattice_96(eng):
 
 # ---- BASELINE configs[2]: batch scoring, no annealing ---------------------------------------------------------------
 def test_batch_scoring_large(eng):
-    d, N, n = 12, 144, 1 << 18
+    d, N, n = 12, 144, 1 << 20                                     # BASELINE configs[2]: 1M structures
     rng = np.random.default_rng(2)
     x = (rng.random((n, N)) < rng.random((n, 1))).astype(np.uint8)
     x[0], x[1] = 0, 1                                               # empty and full lattice

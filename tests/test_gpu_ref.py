@@ -253,3 +253,31 @@ def test_analytical_mode_equals_reference_execution(d):
     assert out["accepted"] == int(z[t + "accept"].sum())
     traj = z[t + "traj"]
     np.testing.assert_allclose(out["trajectory"][1], traj[1], rtol=1e-9, atol=1e-13)
+
+
+def test_island_generator_equals_reference_execution():
+    """drivers/generate_init_structures.py make_random_structure executed upstream (all 48 structures of the fixture)
+    vs the device generator (so_island_structures: NumPy's legacy MT19937 stream restated in the kernel) and the host
+    recipe of so_b200.database."""
+    from so_b200 import engine, database, LSC_cat
+    z = _load("ref_surrogate_sa.npz")
+    lat = engine.Lattice(12, "LSC")
+    got = database.make_random_structures_device(lat, np.arange(48), 48)
+    assert (got == z["train_occs"]).all()
+    cat = LSC_cat(12)
+    for i in (0, 13, 47):
+        assert database.make_random_structure(i, 48, cat) == z["train_occs"][i].tolist()
+    # other sizes / counts: against NumPy's own stream
+    for d, n_strucs, idx in ((20, 10, [0, 3, 9]), (96, 7, [2, 6])):
+        N = d * d
+        lat = engine.Lattice(d, "LSC")
+        got = database.make_random_structures_device(lat, idx, n_strucs)
+        for row, i in zip(got, idx):
+            np.random.seed(i)
+            x = np.zeros(N, dtype=np.uint8)
+            for t in np.random.choice(range(N), size=int(3 + 15 * float(i) / (n_strucs + 1)), replace=False):
+                for a, b in database.ISLAND:
+                    x[((t // d + b) % d) * d + (t % d + a) % d] = 1
+            for s in np.random.choice(range(N), size=16, replace=False):
+                x[s] ^= 1
+            assert (row == x).all()
