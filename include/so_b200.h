@@ -159,6 +159,16 @@ const char *so_kernel_name(int kernel_id);
 int so_set_tscale(so_chains *c, int64_t chain0, int64_t n, const double *tscale);
 int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale);
 
+/* ---- site-type histograms carried through the annealing.  The reference commits "x, syms, OF" per accepted step
+ *      (OML/optimize_SA.py:119-123) and re-types the final structure (drivers/Online_learn_main.py:190); its NH3_cat.flip_atom
+ *      (OML/NH3_cat.py:115-155) was meant to re-type incrementally.  so_track_types(c, 1) makes every SA kernel apply the
+ *      per-flip histogram delta (the rule of so_flip_delta) inside the accept path, so that the LSC type counts {None, 1, 2}
+ *      and the exported NH3 type counts {not exported, 1..7} of every chain are always those of its current structure;
+ *      so_type_histograms reads them (lsc_hist[n][3], nh3_exp[n][8], either may be NULL) without re-typing.
+ *      Any other change of the bits (set_occupancy, flip, randomize, load) recomputes them.  Off by default.        */
+int so_track_types(so_chains *c, int enable);
+int so_type_histograms(so_chains *c, int64_t chain0, int64_t n, int32_t *lsc_hist, int32_t *nh3_exp);
+
 /* ---- checkpoint / resume.  The reference's SA is not resumable (its "checkpoint" is the database folder,
  *      OML/KMC_handler.py:37-42); here a run continues bit for bit from (bits, tscale, step, seed) because the draws are
  *      counter based and the first-layer state is an exact function of the bits.  so_chains_save writes bits + tscale +

@@ -243,6 +243,7 @@ int so_chains_destroy(so_chains *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->bits_dev); cudaFree(c->hq_dev); cudaFree(c->hi_dev); cudaFree(c->lo_dev); cudaFree(c->nact_dev);
   cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch); cudaFree(c->temps_dev);
+  cudaFree(c->type_hist_dev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -266,7 +267,17 @@ struct NvtxRange {
   ~NvtxRange() { nvtxRangePop(); }
 };
 
+// tracked type histograms (so_track_types) follow every change of the bits: recomputed here, carried by the SA kernels
+static int refresh_types(so_chains *c, int64_t chain0, int64_t n) {
+  if (!c->type_hist_dev || n == 0) return SO_OK;
+  const so_lattice *L = c->lat;
+  return so_launch_descriptors(L, c->bits_dev + chain0 * L->W, n, nullptr, nullptr, nullptr,
+                               c->type_hist_dev + c->n_chains * 8 + chain0 * 3, nullptr, c->type_hist_dev + chain0 * 8,
+                               c->stream);
+}
+
 static int rescore(so_chains *c, int64_t chain0, int64_t n) {
+  SO_TRY(refresh_types(c, chain0, n));
   if (!c->sur || n == 0) return SO_OK;
   NvtxRange nvtx_range("state build (first-layer state + objective sums from the bits)");
   const so_lattice *L = c->lat;
@@ -786,6 +797,8 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   if (a->accept_out) SO_TRY(d_acc.alloc(nc * ns));
   SO_CUDA(cudaMemsetAsync(c->counters_dev, 0, 3 * sizeof(unsigned long long), c->stream));
   SaParams P;
+  memset(&P, 0, sizeof(P));
+  P.type_hist = c->type_hist_dev;
   P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
   P.bits = c->bits_dev; P.hq = c->hq_dev; P.hi = c->hi_dev; P.lo = c->lo_dev; P.nact = c->nact_dev;
   P.tscale = c->tscale_dev; P.temps = c->temps_dev;
@@ -841,6 +854,43 @@ int so_get_tscale(so_chains *c, int64_t chain0, int64_t n, double *tscale) {
   SO_REQUIRE(tscale || n == 0, "tscale is NULL");
   SO_CUDA(cudaSetDevice(c->lat->device));
   SO_CUDA(cudaMemcpy(tscale, c->tscale_dev + chain0, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return SO_OK;
+}
+
+// ---- type histograms carried through the annealing (SURVEY 9.5 frozen step order: commit x, h, OF, descriptors) --------
+int so_track_types(so_chains *c, int enable) {
+  SO_REQUIRE(c, "chains handle is NULL");
+  SO_CUDA(cudaSetDevice(c->lat->device));
+  if (!enable) {
+    if (c->type_hist_dev) cudaFree(c->type_hist_dev);
+    c->type_hist_dev = nullptr;
+    return SO_OK;
+  }
+  if (!c->type_hist_dev) {
+    const size_t bytes = (size_t)c->n_chains * 11 * 4;
+    if (cudaMalloc((void **)&c->type_hist_dev, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+      cudaGetLastError();
+      c->type_hist_dev = nullptr;
+      so_set_error("cudaMalloc(%zu bytes) failed for the tracked type histograms", bytes);
+      return SO_ENOMEM;
+    }
+  }
+  SO_TRY(refresh_types(c, 0, c->n_chains));
+  SO_CUDA(cudaStreamSynchronize(c->stream));
+  return SO_OK;
+}
+
+int so_type_histograms(so_chains *c, int64_t chain0, int64_t n, int32_t *lsc_hist, int32_t *nh3_exp) {
+  SO_TRY(check_range(c, chain0, n));
+  SO_REQUIRE(c->type_hist_dev, "type tracking is off (so_track_types)");
+  if (n == 0) return SO_OK;
+  SO_CUDA(cudaSetDevice(c->lat->device));
+  if (nh3_exp)
+    SO_CUDA(cudaMemcpyAsync(nh3_exp, c->type_hist_dev + chain0 * 8, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (lsc_hist)
+    SO_CUDA(cudaMemcpyAsync(lsc_hist, c->type_hist_dev + c->n_chains * 8 + chain0 * 3, (size_t)n * 12, cudaMemcpyDeviceToHost,
+                            c->stream));
+  SO_CUDA(cudaStreamSynchronize(c->stream));
   return SO_OK;
 }
 

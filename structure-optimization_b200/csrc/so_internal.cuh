@@ -67,6 +67,7 @@ struct so_chains {
   size_t temps_cap;
   mutable uint32_t *gate_scratch;       // path index of the resident warps of the cached-gate kernel (so_sa_resident.cu)
   mutable size_t gate_scratch_bytes;
+  int32_t *type_hist_dev;               // tracked histograms: [n_chains][8] NH3 exported + [n_chains][3] LSC, or null
   CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
   int tmap_ok;
 };
@@ -107,6 +108,7 @@ struct SaParams {
                                         // 4 resident warp-per-chain kernel even for few chains, 5 CTA-per-chain kernel
   unsigned long long *counters;
   uint32_t *gate_scratch;
+  int32_t *type_hist;                   // [n_chains][11] tracked type histograms (so_track_types) or null
   SurView sv;
 };
 

@@ -9,6 +9,7 @@
 // which is order independent and therefore reproduced bit-for-bit by oracle/sa.py.  One warp owns one chain;
 // the state streams from HBM (the kernel is bandwidth bound: 4*K*Hp*(1+accept) bytes per flip-evaluation).
 #include "so_internal.cuh"
+#include "so_types.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(256) sa_flat_kernel(SaParams P) {
         ++n_guard;
       }
       if (accept) {
+        if (P.type_hist) so_track_flip(P.type_hist, P.n_chains, c, bits, d, P.N, f, lane);        // before the bit flips
         if (MAXIT > 0) {
 #pragma unroll
           for (int it = 0; it < MAXIT; ++it)
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(128) sa_gated_kernel(SaParams P) {
         ++n_guard;
       }
       if (accept) {
+        if (P.type_hist) so_track_flip(P.type_hist, P.n_chains, c, s_bits, d, P.N, f, lane);      // before the bit flips
         for (int k = lane; k < sv.K; k += 32) {
           int off = __ldg(sv.offs + k);
           int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);

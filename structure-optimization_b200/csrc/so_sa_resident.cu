@@ -16,6 +16,7 @@
 //   * draws come lane-parallel 32 steps at a time (Philox or the injected sequence); the decision uses the fp32
 //     pre-filter of the window kernel and the fp64 rule when that cannot decide.
 #include "so_internal.cuh"
+#include "so_types.cuh"
 #include <math.h>
 
 #define SO_TREE_SMEM_NODES 2048
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
         }
       }
       if (accept) {
+        if (P.type_hist) so_track_flip(P.type_hist, P.n_chains, c, s_bits, d, N, f, lane);        // before the bit flips
         if (GATED && __any_sync(SO_FULL, mywalk != 0)) {     // paths through f are about to change: drop them from the index
           for (int j = 0; j < KW; ++j)
             if ((mywalk >> j) & 1) {
@@ -634,6 +636,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
         }
       }
       if (accept) {                                  // uniform over the CTA
+        if (P.type_hist && warp == 0) so_track_flip(P.type_hist, P.n_chains, c, s_bits, d, N, f, lane);   // before the bit flips
         if (GATED) {
           for (unsigned todo = mywalk; todo; todo &= todo - 1) {
             const int off = s_off[32 * (__ffs(todo) - 1) + lane];

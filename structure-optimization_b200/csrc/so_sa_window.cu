@@ -13,6 +13,7 @@
 //   * Philox and the injected-sequence loads are evaluated lane-parallel for 32 steps at a time; the warp sum uses
 //     three REDUX.SUM on 21-bit limbs; exp() runs in fp64 only when an fp32 pre-filter cannot decide.
 #include "so_window_common.cuh"
+#include "so_types.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
           }
         }
         if (accept) {
+          if (P.type_hist) so_track_flip(P.type_hist, P.n_chains, c, s_bits, d, P.N, f, lane);   // before the bit flips
           if constexpr (COMMIT == 0) {
             asm volatile("" ::: "memory");            // re-read the stage rather than keeping updated values live
 #pragma unroll

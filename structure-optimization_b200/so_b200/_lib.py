@@ -75,6 +75,8 @@ PROTOTYPES = {
     "so_kernel_name": (C.c_char_p, [C.c_int]),
     "so_set_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
     "so_get_tscale": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),
+    "so_track_types": (C.c_int, [C.c_void_p, C.c_int]),
+    "so_type_histograms": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_i32p, c_i32p]),
     "so_chains_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_uint64]),
     "so_chains_load": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, C.POINTER(C.c_uint64)]),
     "so_lsc_analytical": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p, c_f64p]),

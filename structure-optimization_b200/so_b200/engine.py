@@ -321,6 +321,18 @@ class Chains(object):
         B.check(self.lib.so_get_tscale(self.h, chain0, n, _p(t, B.c_f64p)))
         return t
 
+    def track_types(self, enable=True):
+        """Carry the LSC / exported-NH3 type histograms of every chain through accepted flips (so_track_types)."""
+        B.check(self.lib.so_track_types(self.h, int(bool(enable))))
+
+    def type_histograms(self, chain0=0, n=None):
+        """(lsc_hist[n, 3], nh3_exp[n, 8]) of the current structures, as tracked inside the SA kernels (no re-typing)."""
+        n = self.n - chain0 if n is None else n
+        lh = np.empty((n, 3), dtype=np.int32)
+        ne = np.empty((n, 8), dtype=np.int32)
+        B.check(self.lib.so_type_histograms(self.h, chain0, n, _p(lh, B.c_i32p), _p(ne, B.c_i32p)))
+        return lh, ne
+
     def save(self, path, step=0, seed=0):
         """Checkpoint (bits, tscale, exact sums) with the caller's step counter and seed; resume is bit-exact."""
         B.check(self.lib.so_chains_save(self.h, str(path).encode(), int(step), int(seed)))

@@ -500,6 +500,61 @@ def test_best_record_and_objectives_dev(eng):
     assert ms >= 0 and sorted(ch.get_tscale().tolist()) == sorted(P.ladder_tscale(np.arange(n), 6).tolist())
 
 
+@pytest.mark.parametrize("d,descriptor,gated,variant", [(20, "local", False, 3), (12, "local", False, 4), (12, "local", False, 0),
+                                                       (12, "full", True, 4), (12, "full", True, 1), (12, "full", False, 2),
+                                                       (24, "local", True, 3), (12, "full", True, 5)])
+def test_type_histograms_tracked_inside_the_sa_step(eng, d, descriptor, gated, variant):
+    """so_track_types: the LSC / exported-NH3 histograms every SA kernel carries through its accepted flips equal a fresh
+    typing of the final structures (and the oracle's), bit for bit -- window, resident, team, flat, gated and cached-gate
+    kernels; hot chains (about a third of the proposals accepted)."""
+    N, n, steps = d * d, 300, 700
+    if descriptor == "full":
+        p = Hp.golden_surrogate(gated=gated)
+    else:
+        p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=4)
+        if gated:
+            rng = np.random.default_rng(1)
+            feat, thr, left, right, act = [], [], [], [], []
+
+            def node(level):
+                i = len(feat)
+                feat.append(-2); thr.append(0.0); left.append(-1); right.append(-1); act.append(int(rng.random() < 0.6))
+                if level < 5:
+                    feat[i] = int(rng.integers(0, 49)); thr[i] = 0.5
+                    left[i] = node(level + 1); right[i] = node(level + 1)
+                return i
+            node(0)
+            p = S.SurrogateParams(p.offsets, p.W1, p.b1, p.w2, p.b2, p.y_mean, p.y_scale,
+                                  dict(feature=np.array(feat, np.int32), thr=np.array(thr), left=np.array(left, np.int32),
+                                       right=np.array(right, np.int32), active=np.array(act, np.uint8)))
+    lat = eng.Lattice(d, "NH3")
+    ch = eng.Chains(lat, n if variant != 5 else 8)
+    ch.randomize(seed=9, coverage=0.6)
+    ch.attach(Hp.tables_from_params(lat, p))
+    ch.track_types(True)
+    x0 = ch.get_occupancy()
+    lh, ne = ch.type_histograms()
+    t0 = ST.nh3_types(x0, d)
+    assert (ne == ST.nh3_export_hist(t0)).all() and (lh == np.stack([(ST.lsc_types(x0, d) == t).sum(1) for t in range(3)], 1)).all()
+    T_hot = 3.0 * np.abs(ch.objective()).mean() / N if descriptor == "full" else 1.0
+    st = ch.anneal(np.full(steps, T_hot), seed=5, variant=variant)
+    assert st["accepted"] > 0.1 * st["flips"]
+    x1 = ch.get_occupancy()
+    lh, ne = ch.type_histograms()
+    fresh = ch.descriptors(lsc_hist=True, nh3_exp=True)
+    assert (lh == fresh["lsc_hist"]).all() and (ne == fresh["nh3_exp"]).all()
+    assert (ne == ST.nh3_export_hist(ST.nh3_types(x1, d))).all()
+    # explicit flips and re-assignments refresh the tracked counts
+    ch.flip([0, 1], [3, 7])
+    ch.set_occupancy(x0[2:3], chain0=2)
+    lh, ne = ch.type_histograms()
+    fresh = ch.descriptors(lsc_hist=True, nh3_exp=True)
+    assert (lh == fresh["lsc_hist"]).all() and (ne == fresh["nh3_exp"]).all()
+    ch.track_types(False)
+    with pytest.raises(ValueError):
+        ch.type_histograms()
+
+
 def test_checkpoint_resume_is_bit_exact(eng, tmp_path):
     """so_chains_save / so_chains_load: a run cut at a checkpoint and resumed in a NEW handle ends with the same bits,
     sums and temperatures as the uninterrupted run (counter-based draws; the state is an exact function of the bits)."""
