@@ -236,6 +236,24 @@ int so_trainer_get(so_trainer *t, double *W1, double *b1, double *w2, double *b2
 /* MLPRegressor.predict with the current parameters: X [n][K] 0/1 rows -> out [n] (scaled units, fp64) */
 int so_trainer_predict(so_trainer *t, int64_t n, const uint8_t *X, double *out);
 
+/* ---- classifier training on the device (replaces DecisionTreeClassifier(max_depth=30, random_state=0).fit of
+ *      OML/train_surrogate.py:111-114) and the training-set construction before it (:72-98 with the x3 rotation
+ *      augmentation of OML/dynamic_cat.py:270-322).
+ * so_tree_fit: scikit-learn's CART for a 0/1 matrix X[n_rows][K] and class indices y[n_rows] in {0, 1} (two_classes = 0:
+ *   all labels equal), Gini, best splitter, depth-first build, feature order from scikit-learn's xorshift stream seeded
+ *   with splitter_seed (= RandomState(random_state).randint(0, 2^31 - 1)), so that the result is node for node the tree
+ *   scikit-learn fits.  Outputs (capacity max_nodes, SO_EINVAL if exceeded) in scikit-learn's layout: feature (-2 = leaf),
+ *   threshold (0.5 / -2), children_left / children_right (-1 = none), class counts per node; *n_nodes nodes.
+ * so_build_training_set: for n_struct structures (bits[n_struct][words]) the 3N x N matrix of all translations and
+ *   rotations, rows 3*(s*N + r) + k, as bytes into X[n_struct*3N][N] (may be NULL); with site_rates[n_struct][N]: the
+ *   maximum rate (*y_max) and the activity label of every row, active[n_struct*3N] = rate > frac * max (frac = 0.06
+ *   upstream); X_reg / Y_reg of the reference are the rows / tiled rates with active = 1.                      */
+int so_tree_fit(int device, int64_t n_rows, int K, const uint8_t *X, const uint8_t *y, int two_classes, int max_depth,
+                uint32_t splitter_seed, int max_nodes, int32_t *feature, double *threshold, int32_t *children_left,
+                int32_t *children_right, double *count0, double *count1, int32_t *n_nodes, float *kernel_ms);
+int so_build_training_set(so_lattice *lat, int64_t n_struct, const uint32_t *bits, const double *site_rates, double frac,
+                          uint8_t *X, uint8_t *active, double *y_max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,37 @@ void so_set_error(const char *fmt, ...);
     }                                                                                           \
   } while (0)
 
+#define SO_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      so_set_error(__VA_ARGS__);     \
+      return SO_EINVAL;              \
+    }                                \
+  } while (0)
+#define SO_TRY(call)                 \
+  do {                               \
+    int rc__ = (call);               \
+    if (rc__ != SO_OK) return rc__;  \
+  } while (0)
+
+// RAII device buffer for call-scoped staging
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      so_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      return SO_ENOMEM;
+    }
+    return SO_OK;
+  }
+  template <class T> T *as() { return (T *)p; }
+};
+
+
 struct so_lattice {
   int d, N, W, kind, device;
   std::vector<int32_t> rowptr, col;     // host CSR of the 5N-node graph

@@ -91,6 +91,9 @@ PROTOTYPES = {
     "so_trainer_destroy": (C.c_int, [C.c_void_p]),
     "so_trainer_run": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_f64p, C.POINTER(TrainStatus)]),
     "so_trainer_get": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "so_tree_fit": (C.c_int, [C.c_int, C.c_int64, C.c_int, c_u8p, c_u8p, C.c_int, C.c_int, C.c_uint32, C.c_int, c_i32p, c_f64p,
+                              c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, C.POINTER(C.c_float)]),
+    "so_build_training_set": (C.c_int, [C.c_void_p, C.c_int64, c_u32p, c_f64p, C.c_double, c_u8p, c_u8p, c_f64p]),
     "so_trainer_predict": (C.c_int, [C.c_void_p, C.c_int64, c_u8p, c_f64p]),
 }
 

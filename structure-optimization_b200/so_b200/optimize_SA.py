@@ -38,7 +38,7 @@ def default_guard_tol(tables, p_w2_abs_sum, y_scale):
 
 def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0=0.05, cooling='exp', fldr=None,
              n_record=100, prefix='', *, n_chains=1, seed=None, proposals=None, uniforms=None, exact_guard=True,
-             guard_tol=None, gate=True, py2_linear=False, ladder=None, exchange_every=None, gather_every=None,
+             guard_tol=None, gate=True, descriptor=None, py2_linear=False, ladder=None, exchange_every=None, gather_every=None,
              return_stats=False):
     """
     :param cat:        catalyst (LSC_cat / NH3_cat); its occupancy is the start and is replaced by the result
@@ -77,7 +77,8 @@ def optimize(cat, mode='surrogate', surrogate=None, syms=None, n_cycles=100, T_0
     if syms is not None and np.asarray(syms).shape[0] != N:
         raise ValueError('syms must have one row per variable site')
     lattice = cat._lattice
-    tables = surrogate if isinstance(surrogate, engine.SurrogateTables) else tables_for(surrogate, lattice, gate=gate)
+    tables = surrogate if isinstance(surrogate, engine.SurrogateTables) else tables_for(
+        surrogate, lattice, gate=gate, descriptor=descriptor if descriptor is not None else getattr(surrogate, 'descriptor', None))
     chains = engine.Chains(lattice, n_chains)
     chains.set_occupancy(np.repeat(x0[None, :], n_chains, axis=0))
     chains.attach(tables)

@@ -1,15 +1,27 @@
 """
-surrogate -- drop-in for OML/train_surrogate.py:15-184.  The regressor is fitted on the GPU by default (DeviceMLPRegressor: scikit-learn's Adam
-recipe restated in so_train.cu; `on_device=False` calls scikit-learn itself), the tree classifier and the Y scaler
-stay scikit-learn's; the evaluate side (eval_structure_rate, called `eval_rate` by optimize()) runs on the GPU.
+surrogate -- drop-in for OML/train_surrogate.py:15-184.  Training runs on the GPU by default: the activity labels
+(so_build_training_set), the tree classifier (DeviceTreeClassifier: scikit-learn's CART restated in so_tree.cu) and the
+regressor (DeviceMLPRegressor: scikit-learn's Adam recipe restated in so_train.cu); `on_device=False` calls
+scikit-learn itself for both fits.  The 75/25 split permutation and the Y scaler (a mean and a standard deviation) stay
+on the host.  The evaluate side (eval_structure_rate, called `eval_rate` by optimize()) runs on the GPU.
 Upstream defects resolved as in SURVEY 9.5: `Y_scaler` is stored, `train` takes self, both method names exist.
 """
 import numpy as np
 from . import engine
 
 
-def descriptor_offsets(K, d):
-    """Site offsets of the K descriptor columns: full translation row (K == N) or the 7x7 local window (K == 49)."""
+def descriptor_offsets(K, d, descriptor=None):
+    """Site offsets of the K descriptor columns: full translation row (K == N, generate_all_translations order) or the 7x7
+    local window (K == 49, get_local_inds order).  On a 7x7 lattice both have 49 columns in DIFFERENT orders: the caller
+    must then say which one the surrogate was trained on (descriptor='full' | 'local')."""
+    if descriptor not in (None, 'full', 'local'):
+        raise ValueError("descriptor must be 'full' or 'local'")
+    if K == d * d == 49 and descriptor is None:
+        raise ValueError("49 columns on a 7x7 lattice: state descriptor='full' (translation row) or 'local' (7x7 window)")
+    if descriptor == 'local' or (descriptor is None and K == 49 and K != d * d):
+        if K != 49:
+            raise ValueError('the local descriptor has 49 columns, the surrogate has %d' % K)
+        return engine.local_offsets(3)
     if K == d * d:
         return engine.full_offsets(d)
     if K == 49:
@@ -27,7 +39,7 @@ def flatten_tree(classifier):
                 active=(leaf_cls == 1.0).astype(np.uint8))
 
 
-def tables_for(surr, lattice, gate=True):
+def tables_for(surr, lattice, gate=True, descriptor=None):
     """Device tables of any reference-style fitted surrogate (duck type: predictor, Y_scaler, classifier)."""
     mlp = surr.predictor
     if getattr(mlp, 'out_activation_', 'identity') != 'identity' or len(mlp.coefs_) != 2:
@@ -37,9 +49,107 @@ def tables_for(surr, lattice, gate=True):
     scaler = getattr(surr, 'Y_scaler', None)
     y_mean = float(scaler.mean_[0]) if scaler is not None else 0.0
     y_scale = float(scaler.scale_[0]) if scaler is not None else 1.0
-    return engine.SurrogateTables(lattice, descriptor_offsets(W1.shape[0], lattice.d), W1, mlp.intercepts_[0],
+    return engine.SurrogateTables(lattice, descriptor_offsets(W1.shape[0], lattice.d, descriptor), W1, mlp.intercepts_[0],
                                   np.asarray(mlp.coefs_[1]).reshape(-1), float(np.asarray(mlp.intercepts_[1]).reshape(-1)[0]),
                                   y_mean, y_scale, flatten_tree(clf) if clf is not None else None)
+
+
+class _TreeArrays(object):
+    """The fitted-tree attributes of sklearn.tree._tree.Tree that the reference path and flatten_tree() read."""
+
+    def __init__(self, feature, threshold, left, right, count0, count1):
+        self.feature, self.threshold = feature, threshold
+        self.children_left, self.children_right = left, right
+        self.node_count = len(feature)
+        tot = np.maximum(count0 + count1, 1.0)
+        self.n_node_samples = (count0 + count1).astype(np.int64)
+        self.weighted_n_node_samples = count0 + count1
+        self.value = np.stack([count0 / tot, count1 / tot], axis=1)[:, None, :]      # class fractions, as sklearn >= 1.3
+
+
+class DeviceTreeClassifier(object):
+    """The DecisionTreeClassifier(max_depth=30, random_state=0) of OML/train_surrogate.py:111 fitted on the GPU
+    (so_tree_fit): scikit-learn's CART on 0/1 descriptor rows -- Gini, best splitter, depth-first build, the feature
+    order of scikit-learn's own xorshift stream seeded from `random_state` -- so the fitted tree is node for node the one
+    `sklearn.tree.DecisionTreeClassifier(...).fit` returns.  Exposes classes_, tree_ (feature, threshold, children_left,
+    children_right, value, node_count) and predict()."""
+
+    def __init__(self, max_depth=30, random_state=None, device=0, max_nodes=None):
+        self.max_depth, self.random_state, self._device, self._max_nodes = max_depth, random_state, device, max_nodes
+
+    def fit(self, X, y):
+        import ctypes as C
+        from . import _lib as B
+        X = np.asarray(X)
+        Xu = np.ascontiguousarray(X != 0, dtype=np.uint8)
+        if not np.array_equal(Xu, X):
+            raise ValueError('training rows must be 0/1 occupancies')
+        y = np.asarray(y)
+        self.classes_ = np.unique(y)
+        if len(self.classes_) > 2:
+            raise ValueError('the device classifier fits the two-class activity gate of train_surrogate.py')
+        yi = np.ascontiguousarray(np.searchsorted(self.classes_, y), dtype=np.uint8)
+        n, K = Xu.shape
+        rs = self.random_state
+        rng = np.random.mtrand._rand if rs is None else (rs if isinstance(rs, np.random.RandomState) else np.random.RandomState(rs))
+        seed = int(rng.randint(0, 2147483647))                  # Splitter.__cinit__: rand_r_state
+        cap = int(self._max_nodes or min(2 * n + 1, 1 << 20))
+        feature = np.empty(cap, dtype=np.int32)
+        thr = np.empty(cap, dtype=np.float64)
+        left = np.empty(cap, dtype=np.int32)
+        right = np.empty(cap, dtype=np.int32)
+        c0 = np.empty(cap, dtype=np.float64)
+        c1 = np.empty(cap, dtype=np.float64)
+        nn = C.c_int32()
+        ms = C.c_float()
+        depth = 62 if self.max_depth is None else int(self.max_depth)
+        p = lambda a, t: a.ctypes.data_as(t)
+        B.check(B.load().so_tree_fit(int(self._device), n, K, p(Xu, B.c_u8p), p(yi, B.c_u8p), int(len(self.classes_) == 2), depth,
+                                     seed, cap, p(feature, B.c_i32p), p(thr, B.c_f64p), p(left, B.c_i32p), p(right, B.c_i32p),
+                                     p(c0, B.c_f64p), p(c1, B.c_f64p), C.byref(nn), C.byref(ms)))
+        k = nn.value
+        self.kernel_ms_ = ms.value
+        self.tree_ = _TreeArrays(feature[:k].astype(np.int64), thr[:k].copy(), left[:k].astype(np.int64),
+                                 right[:k].astype(np.int64), c0[:k].copy(), c1[:k].copy())
+        self.n_features_in_ = K
+        return self
+
+    def predict(self, X):
+        t = self.tree_
+        X = np.asarray(X)
+        node = np.zeros(len(X), dtype=np.int64)
+        live = t.feature[node] >= 0
+        while live.any():
+            idx = np.nonzero(live)[0]
+            nd = node[idx]
+            go_left = X[idx, t.feature[nd]] <= t.threshold[nd]
+            node[idx] = np.where(go_left, t.children_left[nd], t.children_right[nd])
+            live = t.feature[node] >= 0
+        return self.classes_[np.argmax(t.value[node, 0, :len(self.classes_)], axis=1)]
+
+
+def build_training_set(lattice, occupancies, site_rates=None, frac=0.06, want_rows=True):
+    """all_syms (every translation x 3 rotations of every structure, OML/dynamic_cat.py:270-322), and -- with site rates --
+    the activity label of every row and the maximum rate (OML/train_surrogate.py:72-98), computed on the device
+    (so_build_training_set).  Returns (all_syms float64 [n*3N, N] or None, site_is_active float64 [n*3N] or None, y_max)."""
+    import ctypes as C
+    from . import _lib as B
+    occ = np.asarray(occupancies)
+    if occ.ndim == 1:
+        occ = occ[None, :]
+    n, N = occ.shape
+    bits = engine.pack_bits(occ, lattice.W)
+    X = np.empty((n * 3 * N, N), dtype=np.uint8) if want_rows else None
+    rates = active = None
+    ymax = C.c_double(0.0)
+    if site_rates is not None:
+        rates = np.ascontiguousarray(np.asarray(site_rates, dtype=np.float64).reshape(n, N))
+        active = np.empty(n * 3 * N, dtype=np.uint8)
+    p = lambda a, t: a.ctypes.data_as(t) if a is not None else None
+    B.check(B.load().so_build_training_set(lattice.h, n, p(bits, B.c_u32p), p(rates, B.c_f64p), float(frac), p(X, B.c_u8p),
+                                           p(active, B.c_u8p), C.byref(ymax)))
+    return (X.astype(np.float64) if X is not None else None, active.astype(np.float64) if active is not None else None,
+            ymax.value if rates is not None else None)
 
 
 class DeviceMLPRegressor(object):
@@ -165,16 +275,21 @@ class surrogate(object):
         self.site_is_active = None
         self._device = device
         self._tables = None
+        self._tables_key = None
+        self.descriptor = None              # 'full' | 'local': only needed where K alone is ambiguous (7x7 lattice)
 
     # ---- evaluate (GPU) -----------------------------------------------------------------------------------
     def _get_tables(self, K):
-        if self._tables is None:
+        """Device tables of the CURRENT predictor / classifier / scaler / catalyst (rebuilt when any of them is replaced)."""
+        key = (id(self.predictor), id(self.classifier), id(self.Y_scaler), id(self.cat), K)
+        if self._tables is None or self._tables_key != key:
             if self.cat is not None:
                 lattice = self.cat._lattice
             else:
                 d = int(round(np.sqrt(K)))
                 lattice = engine.Lattice(d if d * d == K and d >= 7 else 12, "LSC", device=self._device)
-            self._tables = tables_for(self, lattice)
+            self._tables = tables_for(self, lattice, descriptor=self.descriptor)
+            self._tables_key = key
         return self._tables
 
     def eval_structure_rate(self, all_trans, normalize=False):
@@ -196,24 +311,37 @@ class surrogate(object):
     def train(self, structure_occs, site_rates, curr_fldr=None, max_iter=10000, random_state=None, verbose=False,
               on_device=True):
         self.all_syms = np.asarray(structure_occs)
-        self.partition_data_set(np.asarray(site_rates))
-        self.train_classifier()
+        self.partition_data_set(np.asarray(site_rates), on_device=on_device)
+        self.train_classifier(on_device=on_device)
         self.train_regressor(max_iter=max_iter, random_state=random_state, verbose=verbose, on_device=on_device)
         self._tables = None
 
-    def partition_data_set(self, site_rates):
+    def partition_data_set(self, site_rates, on_device=True):
+        """OML/train_surrogate.py:72-98: rates tiled x3 (one copy per rotation), active iff rate > 0.06 * max.  on_device:
+        maximum and labels from so_build_training_set (the same float64 comparison), else NumPy as upstream."""
+        site_rates = np.asarray(site_rates, dtype=np.float64)
         flat = np.transpose(np.tile(site_rates.flatten(), [3, 1])).flatten()      # one copy per rotation
-        y_max = np.max(flat)
+        if on_device and self.cat is not None and site_rates.ndim == 2 and site_rates.shape[1] == self.cat.atoms_per_layer:
+            dummy = np.zeros((site_rates.shape[0], site_rates.shape[1]), dtype=np.uint8)
+            _, active, y_max = build_training_set(self.cat._lattice, dummy, site_rates, want_rows=False)
+        else:
+            y_max = np.max(flat)
+            active = (flat > 0.06 * y_max).astype(float)
         if y_max == 0.:
             raise NameError('No active sites in database.')
-        self.site_is_active = (flat > 0.06 * y_max).astype(float)
+        self.site_is_active = active
         self.X_reg = self.all_syms[self.site_is_active == 1]
         self.Y_reg = flat[self.site_is_active == 1]
 
-    def train_classifier(self):
-        from sklearn import tree
+    def train_classifier(self, on_device=True):
+        """OML/train_surrogate.py:101-121.  The 75/25 split is scikit-learn's (one RandomState(0) permutation); the fit runs
+        on the GPU (DeviceTreeClassifier, node for node scikit-learn's tree) or, on_device=False, in scikit-learn itself."""
         from sklearn.model_selection import train_test_split
-        self.classifier = tree.DecisionTreeClassifier(max_depth=30, random_state=0)
+        if on_device:
+            self.classifier = DeviceTreeClassifier(max_depth=30, random_state=0, device=self._device)
+        else:
+            from sklearn import tree
+            self.classifier = tree.DecisionTreeClassifier(max_depth=30, random_state=0)
         X_train, X_test, y_train, y_test = train_test_split(self.all_syms, self.site_is_active, random_state=0)
         self.classifier.fit(X_train, y_train)
         self.frac_wrong_train = float(np.sum(np.abs(self.classifier.predict(X_train) - y_train))) / len(y_train)

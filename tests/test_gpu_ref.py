@@ -281,3 +281,48 @@ def test_island_generator_equals_reference_execution():
             for s in np.random.choice(range(N), size=16, replace=False):
                 x[s] ^= 1
             assert (row == x).all()
+
+
+def test_device_classifier_and_training_set_equal_reference_execution():
+    """Rest of f-2 on the device: all_syms (x3 rotation augmentation) and the activity labels from so_build_training_set,
+    the depth-30 CART from so_tree_fit -- against generate_all_translations_and_rotations / partition_data_set /
+    train_classifier EXECUTED FROM THE REFERENCE SOURCE (the tree of tests/golden/ref_surrogate_sa.npz, node for node)."""
+    from so_b200 import engine, surrogate, LSC_cat
+    from so_b200.train_surrogate import build_training_set, DeviceTreeClassifier, flatten_tree
+    from oracle import tree as OT
+    z = _load("ref_surrogate_sa.npz")
+    d = 12
+    cat = LSC_cat(d)
+    X, active, y_max = build_training_set(cat._lattice, z["train_occs"], z["train_rates"])
+    want = np.vstack([L.generate_all_translations_and_rotations(x, d) for x in z["train_occs"][:3]])
+    assert (X[:len(want)] == want).all() and X.shape == (48 * 3 * 144, 144)
+    assert (active == z["site_is_active"]).all() and y_max == z["train_rates"].max()
+    zd = _load("ref_dynamic_cat.npz")
+    X6, _, _ = build_training_set(engine.Lattice(6, "LSC"), zd["d6_x"][None, :])
+    assert (X6 == zd["d6_all_syms"]).all()                         # the reference's own 108 x 36 matrix
+    sur = surrogate()
+    sur.cat = cat
+    sur.all_syms = X
+    sur.partition_data_set(z["train_rates"])
+    assert (sur.site_is_active == z["site_is_active"]).all() and (sur.Y_reg == z["Y_reg"]).all()
+    sur.train_classifier()                                          # DeviceTreeClassifier
+    assert isinstance(sur.classifier, DeviceTreeClassifier)
+    flat = flatten_tree(sur.classifier)
+    for k, zk in (("feature", "t_feature"), ("thr", "t_thr"), ("left", "t_left"), ("right", "t_right"), ("active", "t_active")):
+        assert (flat[k] == z[zk]).all(), k
+    assert (sur.classifier.predict(X[::7]) == z["clf_train_pred"]).all()
+    # random 0/1 problems: the device tree equals the oracle's restatement of scikit-learn (which tests/test_oracle_tree.py
+    # pins to the installed scikit-learn) -- constant and duplicated columns, shallow depth, one class
+    rng = np.random.default_rng(5)
+    for case in range(6):
+        n, K = int(rng.integers(30, 3000)), int(rng.integers(3, 200))
+        Xr = (rng.random((n, K)) < rng.random()).astype(np.float64)
+        Xr[:, 0] = 1.0
+        Xr[:, K - 1] = Xr[:, 1]
+        y = ((Xr @ rng.normal(size=K) + 0.3 * rng.normal(size=n)) > 0).astype(np.float64) if case < 5 else np.ones(n)
+        depth = (30, 3, 30, 8, 30, 30)[case]
+        t = OT.fit_tree(Xr, y, max_depth=depth, random_state=case % 2)
+        clf = DeviceTreeClassifier(max_depth=depth, random_state=case % 2).fit(Xr, y)
+        assert (clf.tree_.feature == t["feature"]).all() and (clf.tree_.children_left == t["children_left"]).all()
+        assert (clf.tree_.children_right == t["children_right"]).all() and (clf.tree_.threshold == t["threshold"]).all()
+        assert (clf.tree_.n_node_samples == t["count0"] + t["count1"]).all()
