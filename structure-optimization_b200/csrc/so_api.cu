@@ -769,6 +769,13 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
   SaParams P;
   memset(&P, 0, sizeof(P));
   P.type_hist = c->type_hist_dev;
+  {
+    // resident kernel, difference pass: a lane per whole row pays off for the full translation descriptor without a
+    // gate (+12 % at d = 12, K = 144); gated (scattered active rows) and 7x7 windows keep 32/HP4 rows per pass
+    // (profiles/r02_resident_rowlane_ab.txt).  SO_RES_ROWLANE = 0 / 1 forces either.
+    const char *e = getenv("SO_RES_ROWLANE");
+    P.variant_flags = e ? atoi(e) : ((!c->sur->gated && c->sur->K >= 96) ? 1 : 0);
+  }
   P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
   P.bits = c->bits_dev; P.hq = c->hq_dev; P.hi = c->hi_dev; P.lo = c->lo_dev; P.nact = c->nact_dev;
   P.tscale = c->tscale_dev; P.temps = c->temps_dev;

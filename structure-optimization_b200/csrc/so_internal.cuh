@@ -139,6 +139,7 @@ struct SaParams {
                                         // 4 resident warp-per-chain kernel even for few chains, 5 CTA-per-chain kernel
   unsigned long long *counters;
   uint32_t *gate_scratch;
+  int variant_flags;                    // bit 0: resident kernel takes a lane per whole row in the difference pass
   int32_t *type_hist;                   // [n_chains][11] tracked type histograms (so_track_types) or null
   SurView sv;
 };

@@ -298,33 +298,79 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
       }
 
       // relu differences of the rows active on both sides (all rows without a gate)
-      int ax = 0, ay = 0, az = 0, aw = 0;
-      if (worker) {
+      long long acc;
+      if (RES && P.variant_flags) {
+        // state in shared memory: a lane takes WHOLE rows (HP4 x LDS.128 of the state + of the weights, 12 integer ops
+        // per quad) and keeps one int32 accumulator per hidden unit; the second-layer weights enter once per step.
+        // (5 lanes sharing a row, as below, spend most of their instructions on the per-row bookkeeping.)
+        int D[HP4 * 4];
+#pragma unroll
+        for (int j = 0; j < HP4 * 4; ++j) D[j] = 0;
         if (GATED) {
-#pragma unroll 4
-          for (int i = rsub; i < n_list; i += RPP) {
+          for (int i = lane; i < n_list; i += 32) {
             const unsigned e = s_list[i];
             const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
-            const int4 h = hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
-            ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
-            ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
-            az += max(h.z + sg * w.z, 0) - max(h.z, 0);
-            aw += max(h.w + sg * w.w, 0) - max(h.w, 0);
+            const int4 *hr = hq + (e & 0x7fffu) * HP4, *wr = s_W + (e >> 16) * HP4;
+#pragma unroll
+            for (int p = 0; p < HP4; ++p) {
+              const int4 h = hr[p], w = wr[p];
+              D[4 * p + 0] += max(h.x + sg * w.x, 0) - max(h.x, 0);
+              D[4 * p + 1] += max(h.y + sg * w.y, 0) - max(h.y, 0);
+              D[4 * p + 2] += max(h.z + sg * w.z, 0) - max(h.z, 0);
+              D[4 * p + 3] += max(h.w + sg * w.w, 0) - max(h.w, 0);
+            }
           }
         } else {
-#pragma unroll 4
-          for (int k = rsub; k < K; k += RPP) {
+          for (int k = lane; k < K; k += 32) {
             const int off = s_off[k];
             const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
-            const int4 h = hq[row * HP4 + part], w = s_W[k * HP4 + part];
-            ax += max(h.x + sgn * w.x, 0) - max(h.x, 0);
-            ay += max(h.y + sgn * w.y, 0) - max(h.y, 0);
-            az += max(h.z + sgn * w.z, 0) - max(h.z, 0);
-            aw += max(h.w + sgn * w.w, 0) - max(h.w, 0);
+            const int4 *hr = hq + row * HP4, *wr = s_W + k * HP4;
+#pragma unroll
+            for (int p = 0; p < HP4; ++p) {
+              const int4 h = hr[p], w = wr[p];
+              D[4 * p + 0] += max(h.x + sgn * w.x, 0) - max(h.x, 0);
+              D[4 * p + 1] += max(h.y + sgn * w.y, 0) - max(h.y, 0);
+              D[4 * p + 2] += max(h.z + sgn * w.z, 0) - max(h.z, 0);
+              D[4 * p + 3] += max(h.w + sgn * w.w, 0) - max(h.w, 0);
+            }
           }
         }
+        acc = 0;
+#pragma unroll
+        for (int p = 0; p < HP4; ++p) {
+          const int4 v = s_w2[p];
+          acc += (long long)v.x * D[4 * p + 0] + (long long)v.y * D[4 * p + 1] + (long long)v.z * D[4 * p + 2] +
+                 (long long)v.w * D[4 * p + 3];
+        }
+      } else {
+        int ax = 0, ay = 0, az = 0, aw = 0;
+        if (worker) {
+          if (GATED) {
+#pragma unroll 4
+            for (int i = rsub; i < n_list; i += RPP) {
+              const unsigned e = s_list[i];
+              const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
+              const int4 h = hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
+              ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
+              ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
+              az += max(h.z + sg * w.z, 0) - max(h.z, 0);
+              aw += max(h.w + sg * w.w, 0) - max(h.w, 0);
+            }
+          } else {
+#pragma unroll 4
+            for (int k = rsub; k < K; k += RPP) {
+              const int off = s_off[k];
+              const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+              const int4 h = hq[row * HP4 + part], w = s_W[k * HP4 + part];
+              ax += max(h.x + sgn * w.x, 0) - max(h.x, 0);
+              ay += max(h.y + sgn * w.y, 0) - max(h.y, 0);
+              az += max(h.z + sgn * w.z, 0) - max(h.z, 0);
+              aw += max(h.w + sgn * w.w, 0) - max(h.w, 0);
+            }
+          }
+        }
+        acc = (long long)w2.x * ax + (long long)w2.y * ay + (long long)w2.z * az + (long long)w2.w * aw;
       }
-      long long acc = (long long)w2.x * ax + (long long)w2.y * ay + (long long)w2.z * az + (long long)w2.w * aw;
       {  // exact warp sum: |acc| < 2^62 -> three 21-bit limbs, one REDUX each
         int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
         l0 = __reduce_add_sync(SO_FULL, l0);
