@@ -129,13 +129,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
           pend_f = -1;
           __syncwarp();
         }
-        if (lane == 0) {
+        {
           const uint32_t bar = bar0 + pslot * 8, dst = stage0 + pslot * stage_pitch;
-          mbar_expect_tx(bar, stage_bytes);
-          if (use_tma && q1 - gb1 >= 0 && q1 - gb1 + gL <= d && q2 - gb2 >= 0 && q2 - gb2 + gseg <= d)
-            tma_load_3d(dst, &tmap, (q1 - gb1) * (HP4 * 4), q2 - gb2, (int)c, bar);
-          else
-            boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, HP4);
+          const bool interior = use_tma && q1 - gb1 >= 0 && q1 - gb1 + gL <= d && q2 - gb2 >= 0 && q2 - gb2 + gseg <= d;
+          if (lane == 0) {
+            mbar_expect_tx(bar, stage_bytes);
+            if (interior) tma_load_3d(dst, &tmap, (q1 - gb1) * (HP4 * 4), q2 - gb2, (int)c, bar);
+          }
+          if (!interior) boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, HP4, lane);   // warp-uniform
         }
       }
       // ---- 2. step s ---------------------------------------------------------------------------------------
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         int4 *stg = s_stage + slot * stage_i4 + lane;
         if (stale) {                                // the writers' stores are ordered before this by their __syncwarp
           if (COMMIT == 0) {
-            bulk_wait_all();                        // lane 0: every store it issued is complete and visible
+            bulk_wait_all();                        // every lane: the stores it issued are complete and visible
             pend_f = -1;
             __syncwarp();
           }
@@ -220,18 +221,22 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
               }
             }
             fence_async_smem();                       // generic-proxy writes -> visible to the bulk (async proxy) store
-            bulk_wait_all();                          // at most one flip's stores in flight (lane 0 owns the groups)
+            bulk_wait_all();                          // at most one flip's stores in flight (every lane waits for its own groups)
             __syncwarp();
-            if (lane == 0) {
+            {
               const uint32_t src = stage0 + slot * stage_pitch;
-              if (use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d)
-                tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
-              else
-                boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4);
-              bulk_commit();
-              s_bits[f >> 5] ^= (1u << (f & 31));
-              // the stage is re-used by the prefetch issued at the next step: the store must have read it by then
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              const bool interior = use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d;
+              if (interior) {
+                if (lane == 0) tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
+              } else {
+                boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4, lane);     // warp-uniform branch
+              }
+              if (lane == 0 || !interior) {
+                bulk_commit();
+                // the stage is re-used by the prefetch issued at the next step: the store must have read it by then
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              if (lane == 0) s_bits[f >> 5] ^= (1u << (f & 31));
             }
             pend_f = fp;
           } else {

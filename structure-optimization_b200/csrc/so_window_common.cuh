@@ -126,27 +126,33 @@ __device__ __noinline__ int exact_decision_cold(const SurView sv, const uint32_t
   return 0;
 }
 
-// windows that cross the periodic boundary (about 2*(L+n_seg)/d of all flips): n_seg (x2) plain bulk copies, lane 0
+// windows that cross the periodic boundary (about 2*(L+n_seg)/d of all flips): plain bulk copies, one window row per
+// LANE (lanes 0 .. n_seg-1 each issue the one or two copies of their row; all complete on the same mbarrier, whose
+// expect_tx lane 0 posts for the whole window) -- a single pass of the warp instead of a loop in one lane
 __device__ __noinline__ void boundary_loads_cold(const int4 *hq, uint32_t dst, uint32_t bar, int f1, int f2, int b1,
-                                                 int b2, int L, int n_seg, int d, int hp4) {
+                                                 int b2, int L, int n_seg, int d, int hp4, int lane) {
   const uint32_t site_bytes = hp4 * 16;
   int start = f1 - b1;
   if (start < 0) start += d;
   const int n1 = min(L, d - start);
-  for (int sg = 0; sg < n_seg; ++sg) {
+  const int sg = lane;
+  if (sg < n_seg) {
     const int4 *row = hq + (size_t)wrap(f2 - b2 + sg, d) * d * hp4;
     const uint32_t dseg = dst + (uint32_t)(sg * L) * site_bytes;
     bulk_load(dseg, row + (size_t)start * hp4, (uint32_t)n1 * site_bytes, bar);
     if (n1 < L) bulk_load(dseg + (uint32_t)n1 * site_bytes, row, (uint32_t)(L - n1) * site_bytes, bar);
   }
 }
+// the same for the write-back of an accepted flip: lanes 0 .. n_seg-1 each store their row; every issuing lane owns its
+// own bulk group (commit / wait are per thread), so ALL lanes call this and then commit + wait themselves
 __device__ __noinline__ void boundary_stores_cold(int4 *hq, uint32_t src, int f1, int f2, int b1, int b2, int L, int n_seg,
-                                                  int d, int hp4) {
+                                                  int d, int hp4, int lane) {
   const uint32_t site_bytes = hp4 * 16;
   int start = f1 - b1;
   if (start < 0) start += d;
   const int n1 = min(L, d - start);
-  for (int sg = 0; sg < n_seg; ++sg) {
+  const int sg = lane;
+  if (sg < n_seg) {
     int4 *row = hq + (size_t)wrap(f2 - b2 + sg, d) * d * hp4;
     const uint32_t sseg = src + (uint32_t)(sg * L) * site_bytes;
     bulk_store(row + (size_t)start * hp4, sseg, (uint32_t)n1 * site_bytes);
