@@ -774,7 +774,14 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
     // gate (+12 % at d = 12, K = 144); gated (scattered active rows) and 7x7 windows keep 32/HP4 rows per pass
     // (profiles/r02_resident_rowlane_ab.txt).  SO_RES_ROWLANE = 0 / 1 forces either.
     const char *e = getenv("SO_RES_ROWLANE");
-    P.variant_flags = e ? atoi(e) : ((!c->sur->gated && c->sur->K >= 96) ? 1 : 0);
+    P.variant_flags = e ? (atoi(e) & 1) : ((!c->sur->gated && c->sur->K >= 96) ? 1 : 0);
+    // bit 1: gated FULL translation descriptor (column k <-> offset (k % d, k / d)): persistent list of active rows
+    const so_surrogate *su = c->sur;
+    bool full = su->gated && su->K == L->N && (int)su->offs_host.size() == su->K && L->d <= 255;
+    for (int k = 0; full && k < su->K; ++k)
+      full = su->offs_host[k] == (int32_t)(((k / L->d) << 16) | (k % L->d));
+    const char *e2 = getenv("SO_RES_ACTIVE_LIST");
+    if (full && !(e2 && e2[0] == '0')) P.variant_flags |= 2;
   }
   P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
   P.bits = c->bits_dev; P.hq = c->hq_dev; P.hi = c->hi_dev; P.lo = c->lo_dev; P.nact = c->nact_dev;

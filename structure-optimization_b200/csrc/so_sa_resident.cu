@@ -173,6 +173,10 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
   const int4 w2 = worker ? __ldg((const int4 *)sv.w2q + part) : make_int4(0, 0, 0, 0);
   const float tol_f = (float)P.guard_tol;
   const bool guard_on = P.exact_guard != 0;
+  // FULL translation descriptor (K = N, column k <-> offset (k % d, k / d)): every row is affected by every flip, so the
+  // rows that are active are kept in a PERSISTENT compact list (s_list: row | r1 << 16 | r2 << 24, s_pos: position of a
+  // row) that only changes when an accepted flip switches a gate -- the per-step pass over the K rows' gates disappears
+  const bool full = GATED && RES && (P.variant_flags & 2);
 
   for (;;) {
     long long c = 0;
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
     const double tsc = P.tscale[c];
     const float tsc_f = (float)tsc;
     unsigned n_acc = 0, n_guard = 0;
+    int n_alist = 0;               // FULL descriptor: number of active rows in the persistent list
     __syncwarp();
     if (GATED) {      // gates and path index of the starting structure: row r = 32 j + lane -> bit `lane` of word j
       for (int i = lane; i < N * KW; i += 32) s_S[i] = 0u;
@@ -208,6 +213,15 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
         __syncwarp();
         const unsigned m = __ballot_sync(SO_FULL, g);
         if (lane == 0) s_act[r0 >> 5] = m;
+        if (full) {
+          if (g) {
+            const int pos = n_alist + __popc(m & ((1u << lane) - 1u));
+            const int r2 = r / d;
+            s_list[pos] = (unsigned)r | ((unsigned)(r - r2 * d) << 16) | ((unsigned)r2 << 24);
+            s_pos[r] = (unsigned short)pos;
+          }
+          n_alist += __popc(m);
+        }
       }
       __syncwarp();
     }
@@ -249,9 +263,36 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
       int dlo = 0, dn = 0;
 
       // per-lane bit masks over the lane's rows (row of group j: k = 32 j + lane): path tests f / gate changes
-      unsigned mywalk = 0, mychg = 0;
+      unsigned mywalk = 0, mychg = 0, myon = 0;
       int n_list = 0;            // rows active before the flip, compacted: s_list[i] = k << 16 | live << 15 | row
-      if (GATED) {
+      if (GATED && full) {
+        n_list = n_alist;
+        for (int j = 0; j < KW; ++j) mywalk |= ((s_S[f * KW + j] >> lane) & 1u) << j;
+        // only rows whose current path tests site f can change their gate: walk those for the flipped structure
+        for (unsigned todo = mywalk; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1;
+          const int off = s_off[32 * j + lane];
+          const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
+          const int row = r2 * d + r1;
+          const unsigned g0 = (s_act[row >> 5] >> (row & 31)) & 1u;
+          const unsigned g1 = walk1(s_tree, s_bits, d, f, r1, r2);
+          mychg |= (g0 ^ g1) << j;
+          myon |= g1 << j;
+        }
+        __syncwarp();
+        // a row that switches contributes its whole NEW row sum: + if it switches on (it is not in the list), - if it
+        // switches off (it stays in the list for this step and contributes new - old there: the total is - old)
+        for (unsigned todo = mychg; todo; todo &= todo - 1) {
+          const int j = __ffs(todo) - 1, k = 32 * j + lane;
+          const int off = s_off[k];
+          const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
+          const long long A = row_sum_res<HP4>(hq + row * HP4, s_W + k * HP4, s_w2, sgn);
+          const int sg = ((myon >> j) & 1) ? 1 : -1;
+          dhi += sg * (A >> SO_SPLIT_BITS);
+          dlo += sg * (int)(A & SO_SPLIT_MASK);
+          dn += sg;
+        }
+      } else if (GATED) {
         unsigned g0m = 0;
         const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 2
@@ -299,7 +340,7 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
 
       // relu differences of the rows active on both sides (all rows without a gate)
       long long acc;
-      if (RES && P.variant_flags) {
+      if (RES && (P.variant_flags & 1)) {
         // state in shared memory: a lane takes WHOLE rows (HP4 x LDS.128 of the state + of the weights, 12 integer ops
         // per quad) and keeps one int32 accumulator per hidden unit; the second-layer weights enter once per step.
         // (5 lanes sharing a row, as below, spend most of their instructions on the per-row bookkeeping.)
@@ -309,8 +350,15 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
         if (GATED) {
           for (int i = lane; i < n_list; i += 32) {
             const unsigned e = s_list[i];
-            const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
-            const int4 *hr = hq + (e & 0x7fffu) * HP4, *wr = s_W + (e >> 16) * HP4;
+            int row, k, sg;
+            if (full) {
+              row = e & 0xffffu; sg = sgn;
+              k = wrap(f2 - (int)(e >> 24), d) * d + wrap(f1 - (int)((e >> 16) & 0xffu), d);
+            } else {
+              row = e & 0x7fffu; k = e >> 16;
+              sg = sgn & -(int)((e >> 15) & 1u);              // branch-free: a row that just switched off sees weight 0
+            }
+            const int4 *hr = hq + row * HP4, *wr = s_W + k * HP4;
 #pragma unroll
             for (int p = 0; p < HP4; ++p) {
               const int4 h = hr[p], w = wr[p];
@@ -349,8 +397,15 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
 #pragma unroll 4
             for (int i = rsub; i < n_list; i += RPP) {
               const unsigned e = s_list[i];
-              const int sg = sgn & -(int)((e >> 15) & 1u);      // branch-free: a row that just switched off sees weight 0
-              const int4 h = hq[(e & 0x7fffu) * HP4 + part], w = s_W[(e >> 16) * HP4 + part];
+              int row, k, sg;
+              if (full) {
+                row = e & 0xffffu; sg = sgn;
+                k = wrap(f2 - (int)(e >> 24), d) * d + wrap(f1 - (int)((e >> 16) & 0xffu), d);
+              } else {
+                row = e & 0x7fffu; k = e >> 16;
+                sg = sgn & -(int)((e >> 15) & 1u);            // branch-free: a row that just switched off sees weight 0
+              }
+              const int4 h = hq[row * HP4 + part], w = s_W[k * HP4 + part];
               ax += max(h.x + sg * w.x, 0) - max(h.x, 0);
               ay += max(h.y + sg * w.y, 0) - max(h.y, 0);
               az += max(h.z + sg * w.z, 0) - max(h.z, 0);
@@ -436,6 +491,32 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
             const int off = s_off[32 * (__ffs(todo) - 1) + lane];
             const int row = wrap(f2 - (off >> 16), d) * d + wrap(f1 - (int)(short)(off & 0xffff), d);
             atomicXor(s_act + (row >> 5), 1u << (row & 31));
+          }
+          if (full) {       // persistent list: append the rows that switched on, swap-remove those that switched off
+            for (unsigned lanes = __ballot_sync(SO_FULL, mychg != 0); lanes; lanes &= lanes - 1) {
+              const int l = __ffs(lanes) - 1;
+              const unsigned o = __shfl_sync(SO_FULL, myon, l);
+              for (unsigned m = __shfl_sync(SO_FULL, mychg, l); m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const int off = s_off[32 * j + l];
+                const int r1 = wrap(f1 - (int)(short)(off & 0xffff), d), r2 = wrap(f2 - (off >> 16), d);
+                const int row = r2 * d + r1;
+                const bool on = (o >> j) & 1u;
+                if (lane == 0) {
+                  if (on) {
+                    s_list[n_alist] = (unsigned)row | ((unsigned)r1 << 16) | ((unsigned)r2 << 24);
+                    s_pos[row] = (unsigned short)n_alist;
+                  } else {
+                    const int ppos = s_pos[row];
+                    const unsigned last = s_list[n_alist - 1];
+                    s_list[ppos] = last;
+                    s_pos[last & 0xffffu] = (unsigned short)ppos;
+                  }
+                }
+                n_alist += on ? 1 : -1;
+                __syncwarp();
+              }
+            }
           }
         }
         if (lane == 0) s_bits[f >> 5] ^= (1u << (f & 31));
