@@ -182,7 +182,9 @@ def workload_config(a, cores_note=None):
            "step": "one sweep = %d Metropolis steps per chain" % (a.sweep_steps if a.sweep_steps > 0 else a.d * a.d),
            "l2_policy": "working set (%.1f GB of per-chain state) >> 126 MB L2; no flush needed" % (
                a.chains * a.d * a.d * H * 4 / 1e9),
-           "rng": "Philox4x32-10, key=seed, counter=(step, chain)"}
+           "rng": "Philox4x32-10, key=seed, counter=(step, chain)",
+           "state": ("first-layer state packed to 24 bits per hidden unit, 64 B per site (scores within 1e-5 of fp64)"
+                     if a.compact else "first-layer state int32, 80 B per site")}
     if cores_note:
         cfg["note"] = cores_note
     return cfg
@@ -337,7 +339,7 @@ def run_gpu(a):
     lat = engine.Lattice(d, "NH3", device=local_rank)
     offsets = engine.local_offsets(3)
     W1, b1, w2, b2 = glorot_mlp(offsets, H, 0)
-    tab = engine.SurrogateTables(lat, offsets, W1, b1, w2, b2)
+    tab = engine.SurrogateTables(lat, offsets, W1, b1, w2, b2, compact=bool(a.compact))
     ch = engine.Chains(lat, n_local)
     ch.randomize(seed=1234 + rank, coverage=0.5)
     ch.attach(tab)
@@ -456,14 +458,16 @@ def run_gpu(a):
             tj = json.load(open(tpath))
             sh = tj.get("shape", {})
             if (sh.get("lattice") == "%dx%d" % (d, d) and sh.get("chains") == n_local and sh.get("steps_per_launch") == N
-                    and str(kernel_name) in str(sh.get("kernel"))):
+                    and str(kernel_name) in str(sh.get("kernel")) and bool(sh.get("compact", False)) == bool(a.compact)):
                 traffic = tj.get("sa_window_kernel")
         except Exception:
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32 fixed-point state / int64 sums / f64 Metropolis",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("24-bit packed fixed-point state / int64 sums / f64 Metropolis" if a.compact else
+                  "int32 fixed-point state / int64 sums / f64 Metropolis"),
         "data": "synthetic", "config": workload_config(a),
         "accept_fraction": acc_frac, "clocks": clk.summary(), "e2e": e2e,
         # SA kernel per sweep (+ arg-max kernel of the all-gather, + objective/decision/commit kernels of a swap round)
@@ -471,8 +475,16 @@ def run_gpu(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": kernel_name,
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                     "launch_ms": kern_ms / a.steps},
+                     "launch_ms": kern_ms / a.steps,
+                     "note": "achieved / frac count SURVEY 8(d)'s algorithmic bytes (4*K*H*(1+a) + 15 + 4a: an int32 state)"},
     }
+    if a.compact:
+        # the kernel actually moves 64 instead of 80 bytes per site: the same rate in bytes of the packed layout
+        b_packed = 64.0 * K_WIN * (1.0 + acc_frac) + 15.0 + 4.0 * acc_frac
+        line["roofline"]["packed_state"] = {"bytes_per_flip": b_packed, "achieved": achieved * b_packed / b_alg,
+                                            "frac": achieved * b_packed / b_alg / peak,
+                                            "what": "24-bit packed first-layer state, 64 B per site, records aligned with the "
+                                                    "64-B L2 fill granule (DESIGN.md section 4)"}
     if gather is not None:
         line["collective_ms_per_step"] = coll_ms / a.steps
         line["best_structure"] = {"of": gather.best[0], "chain": gather.best[1]}
@@ -481,6 +493,19 @@ def run_gpu(a):
         line["pt_self_check"] = pt_check
     if world == 1 and pt is None and a.accept_sweep:
         line["accept_sweep"] = accept_sweeps(ch, a, N, chain_id0, peak)
+    if world == 1 and pt is None and a.compact and a.accept_sweep:
+        # the same workload on the int32 state (80 B per site; the round-1 layout), same box, untimed tail
+        tab32 = engine.SurrogateTables(lat, offsets, W1, b1, w2, b2, compact=False)
+        ch.randomize(seed=1234 + rank, coverage=0.5)
+        ch.attach(tab32)
+        for s_ in range(a.warmup + 1):
+            st32 = ch.anneal(temps_all[s_ * N:(s_ + 1) * N], step0=s_ * N, seed=a.seed, chain_id0=chain_id0)
+        a32 = st32["accepted"] / max(st32["flips"], 1)
+        b32 = 4.0 * K_WIN * H * (1.0 + a32) + 15.0 + 4.0 * a32
+        v32 = st32["flips"] / (st32["kernel_ms"] * 1e-3)
+        line["int32_state"] = {"value": v32, "unit": UNIT, "ms": st32["kernel_ms"], "accept_fraction": a32,
+                               "frac": v32 * b32 / 1e9 / peak, "kernel": st32["kernel"],
+                               "what": "sweep %d of the same schedule with the int32 first-layer state (--compact 0)" % a.warmup}
     if world == 1 and pt is None and a.other_configs:
         ch.close()
         line["other_configs"] = other_configs()
@@ -610,6 +635,8 @@ def main():
     ap.add_argument("--gather-every", type=int, default=0, help="best-structure all-gather period in sweeps (0 = 10 with PT, 1 without)")
     ap.add_argument("--ladder", type=int, default=8, help="parallel-tempering ladder size")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--compact", type=int, default=1,
+                    help="1 (default): 24-bit packed first-layer state, 64 B per site (so_surrogate_create_compact); 0: int32 state")
     ap.add_argument("--other-configs", type=int, default=1, help="1: also record BASELINE configs[1] and configs[2] numbers")
     ap.add_argument("--accept-sweep", type=int, default=1, help="1: also time one sweep at accept fractions 0.5/0.2/0.05")
     ap.add_argument("--cpu-flips", type=int, default=3000, help="Metropolis steps per core for the CPU baseline (0 = skip)")

@@ -98,6 +98,16 @@ int so_surrogate_create(so_lattice *lat, int K, int H, const int32_t *offsets, c
                         int n_tree_nodes, const int32_t *feature, const double *thr, const int32_t *left,
                         const int32_t *right, const uint8_t *leaf_active, so_surrogate **out);
 int so_surrogate_destroy(so_surrogate *s);
+/* the same surrogate with a COMPACT first-layer state: the power-of-two grid of the first layer is 2^8 coarser
+ * (|pre-activation| < 2^23 grid units), so that a site's 20 pre-activations pack into 64 bytes (five 24-bit values per
+ * 16 bytes) instead of 80.  Records then coincide with the 64-byte fill granule of the L2: a flip moves 3,136 bytes of
+ * DRAM traffic instead of ~4,480.  Scores stay within the 1e-5 bar (tests); decisions are those of the same exact
+ * integer arithmetic on the coarser grid, re-taken from the fp64 weights near ties when exact_guard is set.  Needs 17..20
+ * hidden units, a rectangular-window descriptor (e.g. get_local_inds) and no tree gate; so_anneal then always runs the
+ * pipelined window kernel.                                                                                       */
+int so_surrogate_create_compact(so_lattice *lat, int K, int H, const int32_t *offsets, const double *W1,
+                                const double *b1, const double *W2, double b2, double y_mean, double y_scale,
+                                so_surrogate **out);
 /* quantisation exponents chosen at load: h grid 2^e_h, w2 grid 2^e_w, padded hidden width Hp              */
 int so_surrogate_info(const so_surrogate *s, int *K, int *H, int *Hp, int *e_h, int *e_w, int *gated);
 

@@ -145,12 +145,21 @@ def ceil_log2(x):
     return e - 1 if m == 0.5 else e
 
 
-def quantize(p):
-    """Power-of-two fixed-point grids for layer 1 (int32 pre-activations) and layer 2 (int64 dot)."""
+def quantize(p, bits=30):
+    """Power-of-two fixed-point grids for layer 1 (int32 pre-activations) and layer 2 (int64 dot).  bits = 30: the int32
+    state; bits = 'packed24': the grid of the 24-bit packed state (so_surrogate_create_compact)."""
     Hp = (p.H + 3) // 4 * 4
     bound = float(np.max(np.abs(p.b1) + np.abs(p.W1).sum(0)))
     bound = max(bound, 2.0 ** -100)
-    e_h = ceil_log2(bound) - 30          # |h|/2^e_h <= 2^30 (+ (K+1)/2 rounding slack < 2^31)
+    if bits == "packed24":
+        # 24-bit packed state of the CUDA path: the finest power-of-two grid with max_j sum_k |rint(W1_kj / grid)| < 2^24
+        # (the stored value is hq minus the smallest reachable hq of the unit, so only the L1 range counts)
+        e_h = ceil_log2(max(float(np.max(np.abs(p.W1).sum(0))), 2.0 ** -100)) - 24
+        while int(np.abs(np.rint(np.ldexp(p.W1, -e_h))).sum(0).max()) >= 2 ** 24:
+            e_h += 1
+        bits = 30
+    else:
+        e_h = ceil_log2(bound) - bits    # |h|/2^e_h <= 2^bits (+ (K+1)/2 rounding slack < 2^(bits+1))
     w_bits = 31 - ceil_log2(float(Hp))          # |A_r| <= Hp * 2^w_bits * 2^31 <= 2^62
     wmax = max(float(np.max(np.abs(p.w2))), 2.0 ** -100)
     e_w = ceil_log2(wmax) - w_bits
@@ -160,7 +169,7 @@ def quantize(p):
     W1q[:, :p.H] = np.rint(np.ldexp(p.W1, -e_h)).astype(np.int64)
     b1q[:p.H] = np.rint(np.ldexp(p.b1, -e_h)).astype(np.int64)
     w2q[:p.H] = np.rint(np.ldexp(p.w2, -e_w)).astype(np.int64)
-    assert int(np.abs(b1q.astype(np.int64)).max() + np.abs(W1q.astype(np.int64)).sum(0).max()) < 2 ** 31
+    assert int(np.abs(b1q.astype(np.int64)).max() + np.abs(W1q.astype(np.int64)).sum(0).max()) < 2 ** (bits + 1)
     return dict(Hp=Hp, e_h=e_h, e_w=e_w, W1q=W1q, b1q=b1q, w2q=w2q, c=math.ldexp(1.0, e_h + e_w))
 
 

@@ -214,6 +214,7 @@ int so_chains_destroy(so_chains *c) {
   cudaFree(c->bits_dev); cudaFree(c->hq_dev); cudaFree(c->hi_dev); cudaFree(c->lo_dev); cudaFree(c->nact_dev);
   cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch); cudaFree(c->temps_dev);
   cudaFree(c->type_hist_dev);
+  cudaFree(c->tmp_hq_dev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -251,6 +252,28 @@ static int rescore(so_chains *c, int64_t chain0, int64_t n) {
   if (!c->sur || n == 0) return SO_OK;
   NvtxRange nvtx_range("state build (first-layer state + objective sums from the bits)");
   const so_lattice *L = c->lat;
+  if (c->sur->compact) {
+    // the scorers write int32 [site][20]; slabs of it are packed to 24 bits / 64 bytes per site (so_sa_window.cu)
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n, (1LL << 30) / ((int64_t)L->N * 80)));
+    if ((int64_t)c->tmp_hq_chains < slab) {
+      cudaFree(c->tmp_hq_dev);
+      c->tmp_hq_dev = nullptr; c->tmp_hq_chains = 0;
+      if (cudaMalloc((void **)&c->tmp_hq_dev, (size_t)slab * L->N * 80) != cudaSuccess) {
+        cudaGetLastError();
+        so_set_error("cudaMalloc failed for the state-build staging slab");
+        return SO_ENOMEM;
+      }
+      c->tmp_hq_chains = (size_t)slab;
+    }
+    for (int64_t c0 = 0; c0 < n; c0 += slab) {
+      const int64_t nc = std::min(slab, n - c0);
+      SO_TRY(so_launch_score(L, c->sur, c->bits_dev + (chain0 + c0) * L->W, nc, c->tmp_hq_dev, c->hi_dev + chain0 + c0,
+                             c->lo_dev + chain0 + c0, c->nact_dev + chain0 + c0, c->stream));
+      SO_TRY(so_launch_pack24(c->tmp_hq_dev, (char *)c->hq_dev + (size_t)(chain0 + c0) * L->N * 64, nc * L->N, c->sur->bias24_dev,
+                              c->stream));
+    }
+    return SO_OK;
+  }
   return so_launch_score(L, c->sur, c->bits_dev + chain0 * L->W, n,
                          c->hq_dev + chain0 * (long long)L->N * c->sur->Hp, c->hi_dev + chain0, c->lo_dev + chain0,
                          c->nact_dev + chain0, c->stream);
@@ -445,11 +468,12 @@ int so_flip_delta(so_chains *c, int64_t chain0, int64_t n, const int32_t *sites,
 }
 
 // ---- surrogate ------------------------------------------------------------------------------------------
-int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, const double *W1, const double *b1,
-                        const double *W2, double b2, double y_mean, double y_scale, int n_tree_nodes,
-                        const int32_t *feature, const double *thr, const int32_t *left, const int32_t *right,
-                        const uint8_t *leaf_active, so_surrogate **out) {
+static int surrogate_create_impl(so_lattice *L, int K, int H, const int32_t *offsets, const double *W1, const double *b1,
+                                 const double *W2, double b2, double y_mean, double y_scale, int n_tree_nodes,
+                                 const int32_t *feature, const double *thr, const int32_t *left, const int32_t *right,
+                                 const uint8_t *leaf_active, int state_bits, so_surrogate **out) {
   SO_REQUIRE(L && offsets && W1 && b1 && W2 && out, "NULL argument");
+  SO_REQUIRE(state_bits == 30 || state_bits == 22, "state_bits must be 30 (int32 state) or 22 (24-bit packed state)");
   SO_REQUIRE(K >= 1 && H >= 1 && H <= 32, "surrogate shape K=%d H=%d not supported (1 <= H <= 32)", K, H);
   SO_REQUIRE(n_tree_nodes >= 0, "negative tree size");
   SO_REQUIRE(n_tree_nodes == 0 || (feature && thr && left && right && leaf_active), "tree arrays missing");
@@ -489,7 +513,30 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
   }
   bound = std::max(bound, ldexp(1.0, -100));
   wmax = std::max(wmax, ldexp(1.0, -100));
-  s->e_h = ceil_log2(bound) - 30;
+  s->e_h = ceil_log2(bound) - 30;               // |hq| <= 2^30 (+ rounding slack), oracle: quantize()
+  s->compact = state_bits == 22;
+  s->Wst24_dev = nullptr; s->bias24_dev = nullptr;
+  if (s->compact) {
+    // packed state: 24 bits hold hq - (smallest reachable hq) of every unit, i.e. the unit's L1 range sum_k |W1q_kj|:
+    // the grid is the finest power of two with max_j sum_k |rint(W1_kj / grid)| < 2^24 (oracle: quantize(bits='packed24'))
+    double l1max = ldexp(1.0, -100);
+    for (int j = 0; j < H; ++j) {
+      double sum = 0.0;
+      for (int k = 0; k < K; ++k) sum += fabs(W1[(size_t)k * H + j]);
+      l1max = std::max(l1max, sum);
+    }
+    s->e_h = ceil_log2(l1max) - 24;
+    for (;;) {
+      long long worst = 0;
+      for (int j = 0; j < H; ++j) {
+        long long sum = 0;
+        for (int k = 0; k < K; ++k) sum += llabs((long long)nearbyint(ldexp(W1[(size_t)k * H + j], -s->e_h)));
+        worst = std::max(worst, sum);
+      }
+      if (worst < (1LL << 24)) break;
+      ++s->e_h;
+    }
+  }
   int w_bits = 31 - ceil_log2((double)s->Hp);
   s->e_w = ceil_log2(wmax) - w_bits;
   s->c = ldexp(1.0, s->e_h + s->e_w);
@@ -532,6 +579,26 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
     }
   }
   if (rc == SO_OK) rc = upload(&s->Wst_dev, Wst.data(), (size_t)K * Hp);
+  if (s->compact) {
+    // the packed state serves the pipelined window kernel only: 17..20 hidden units, rectangular window, no gate
+    if (!(Hp == 20 && s->win_ok && !s->gated)) {
+      so_surrogate_destroy(s);
+      so_set_error("the compact (24-bit) state needs 17..20 hidden units, a rectangular-window descriptor and no tree gate");
+      return SO_EINVAL;
+    }
+    std::vector<int32_t> bias(Hp, 0);
+    for (int j = 0; j < Hp; ++j) {
+      long long lo = s->b1q_host[j];
+      for (int k = 0; k < K; ++k) lo += std::min<int32_t>(s->W1q_host[(size_t)k * Hp + j], 0);
+      bias[j] = (int32_t)(-lo);
+    }
+    if (rc == SO_OK) rc = upload(&s->bias24_dev, bias.data(), bias.size());
+    std::vector<int32_t> W24((size_t)K * 4 * 8, 0);           // slot q = site p * 4 + part: weights of units 5*part .. 5*part+4
+    for (int p = 0; p < K; ++p)
+      for (int part = 0; part < 4; ++part)
+        for (int i = 0; i < 5; ++i) W24[((size_t)p * 4 + part) * 8 + i] = Wst[(size_t)p * Hp + 5 * part + i];
+    if (rc == SO_OK) rc = upload(&s->Wst24_dev, W24.data(), W24.size());
+  }
   if (rc == SO_OK) rc = upload(&s->offs_dev, s->offs_host.data(), (size_t)K);
   if (rc == SO_OK) rc = upload(&s->W1q_dev, s->W1q_host.data(), (size_t)K * Hp);
   if (rc == SO_OK) rc = upload(&s->b1q_dev, s->b1q_host.data(), (size_t)Hp);
@@ -563,9 +630,24 @@ int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, con
   return SO_OK;
 }
 
+int so_surrogate_create(so_lattice *L, int K, int H, const int32_t *offsets, const double *W1, const double *b1,
+                        const double *W2, double b2, double y_mean, double y_scale, int n_tree_nodes,
+                        const int32_t *feature, const double *thr, const int32_t *left, const int32_t *right,
+                        const uint8_t *leaf_active, so_surrogate **out) {
+  return surrogate_create_impl(L, K, H, offsets, W1, b1, W2, b2, y_mean, y_scale, n_tree_nodes, feature, thr, left, right,
+                               leaf_active, 30, out);
+}
+
+int so_surrogate_create_compact(so_lattice *L, int K, int H, const int32_t *offsets, const double *W1, const double *b1,
+                                const double *W2, double b2, double y_mean, double y_scale, so_surrogate **out) {
+  return surrogate_create_impl(L, K, H, offsets, W1, b1, W2, b2, y_mean, y_scale, 0, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, 22, out);
+}
+
 int so_surrogate_destroy(so_surrogate *s) {
   if (!s) return SO_OK;
   cudaSetDevice(s->device);
+  cudaFree(s->Wst24_dev); cudaFree(s->bias24_dev);
   cudaFree(s->tc_image_dev); cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
   cudaFree(s->W1d_dev); cudaFree(s->b1d_dev); cudaFree(s->w2d_dev);
   cudaFree(s->t_feature_dev); cudaFree(s->t_thr_dev); cudaFree(s->t_left_dev); cudaFree(s->t_right_dev);
@@ -592,7 +674,8 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
   SO_CUDA(cudaSetDevice(L->device));
   cudaFree(c->hq_dev); cudaFree(c->hi_dev); cudaFree(c->lo_dev); cudaFree(c->nact_dev);
   c->hq_dev = nullptr; c->hi_dev = c->lo_dev = nullptr; c->nact_dev = nullptr; c->sur = nullptr;
-  size_t bytes = (size_t)c->n_chains * L->N * s->Hp * 4;
+  const int site_words = s->compact ? 16 : s->Hp;          // uint32 per site in memory
+  size_t bytes = (size_t)c->n_chains * L->N * site_words * 4;
   cudaError_t e = cudaMalloc(&c->hq_dev, bytes);
   if (e == cudaSuccess) e = cudaMalloc(&c->hi_dev, (size_t)c->n_chains * 8);
   if (e == cudaSuccess) e = cudaMalloc(&c->lo_dev, (size_t)c->n_chains * 8);
@@ -609,7 +692,7 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
   c->tmap_ok = 0;
   if (s->win_ok && !s->gated) {
     const int Lw = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
-    if ((uint64_t)Lw * s->Hp <= 256 && nseg <= 256) {
+    if ((uint64_t)Lw * site_words <= 256 && nseg <= 256) {
       typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -617,9 +700,9 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
       cudaDriverEntryPointQueryResult qres;
       if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
           qres == cudaDriverEntryPointSuccess) {
-        cuuint64_t gdim[3] = {(cuuint64_t)L->d * s->Hp, (cuuint64_t)L->d, (cuuint64_t)c->n_chains};
-        cuuint64_t gstr[2] = {(cuuint64_t)L->d * s->Hp * 4, (cuuint64_t)L->N * s->Hp * 4};
-        cuuint32_t box[3] = {(cuuint32_t)(Lw * s->Hp), (cuuint32_t)nseg, 1};
+        cuuint64_t gdim[3] = {(cuuint64_t)L->d * site_words, (cuuint64_t)L->d, (cuuint64_t)c->n_chains};
+        cuuint64_t gstr[2] = {(cuuint64_t)L->d * site_words * 4, (cuuint64_t)L->N * site_words * 4};
+        cuuint32_t box[3] = {(cuuint32_t)(Lw * site_words), (cuuint32_t)nseg, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult cr = ((EncodeFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, c->hq_dev, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -668,6 +751,15 @@ int so_get_preact(so_chains *c, int64_t chain, int32_t *hq) {
   SO_REQUIRE(c->sur && hq, "no surrogate attached or NULL output");
   SO_CUDA(cudaSetDevice(c->lat->device));
   size_t row = (size_t)c->lat->N * c->sur->Hp;
+  if (c->sur->compact) {
+    DevBuf tmp;
+    SO_TRY(tmp.alloc(row * 4));
+    SO_TRY(so_launch_unpack24((const char *)c->hq_dev + (size_t)chain * c->lat->N * 64, tmp.as<int32_t>(), c->lat->N,
+                              c->sur->bias24_dev, c->stream));
+    SO_CUDA(cudaMemcpyAsync(hq, tmp.p, row * 4, cudaMemcpyDeviceToHost, c->stream));
+    SO_CUDA(cudaStreamSynchronize(c->stream));
+    return SO_OK;
+  }
   SO_CUDA(cudaMemcpy(hq, c->hq_dev + (size_t)chain * row, row * 4, cudaMemcpyDeviceToHost));
   return SO_OK;
 }

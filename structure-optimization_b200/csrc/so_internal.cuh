@@ -75,6 +75,9 @@ struct so_surrogate {
   std::vector<int32_t> W1q_host, b1q_host, w2q_host, offs_host;
   int win_ok, win_a1, win_b1, win_a2, win_b2;   // descriptor offsets form the full rectangle [a1,b1] x [a2,b2]
   int32_t *Wst_dev;                             // W1q rows in staged (memory) order of the window
+  int compact;                                  // 24-bit packed state, 64 bytes per site (so_surrogate_create_compact)
+  int32_t *bias24_dev;                          // compact: [Hp] stored value = hq + bias
+  int32_t *Wst24_dev;                           // compact: [K*4 slots][8] = five weights of the slot's hidden units + pad
   unsigned char *tc_image_dev;                  // B operand of the tensor-core scorer (so_score_tc.cu) or NULL
   int tc_ok;
 };
@@ -98,6 +101,8 @@ struct so_chains {
   size_t temps_cap;
   mutable uint32_t *gate_scratch;       // path index of the resident warps of the cached-gate kernel (so_sa_resident.cu)
   mutable size_t gate_scratch_bytes;
+  int32_t *tmp_hq_dev;                  // compact state: int32 staging slab of the state build
+  size_t tmp_hq_chains;
   int32_t *type_hist_dev;               // tracked histograms: [n_chains][8] NH3 exported + [n_chains][3] LSC, or null
   CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
   int tmap_ok;
@@ -114,6 +119,7 @@ struct SurView {
   const int32_t *t_feature, *t_left, *t_right;
   const double *t_thr;
   const uint8_t *t_active;
+  const int32_t *bias24;                // compact state: per-unit storage bias
   const int4 *t_packed;                 // flags: 1 leaf, 2 leaf is active, 4 go left when the bit is 0, 8 ... when it is 1; bits 8.. = column tested
   int n_tree;
 };
@@ -148,6 +154,7 @@ inline SurView make_view(const so_surrogate *s) {
   SurView v;
   v.K = s->K; v.Hp = s->Hp; v.HP4 = s->HP4; v.gated = s->gated; v.H = s->H;
   v.c = s->c; v.b2 = s->b2; v.y_mean = s->y_mean; v.y_scale = s->y_scale;
+  v.bias24 = s->bias24_dev;
   v.offs = s->offs_dev; v.W1q = s->W1q_dev; v.b1q = s->b1q_dev; v.w2q = s->w2q_dev;
   v.W1d = s->W1d_dev; v.b1d = s->b1d_dev; v.w2d = s->w2d_dev;
   v.t_feature = s->t_feature_dev; v.t_left = s->t_left_dev; v.t_right = s->t_right_dev;
@@ -177,10 +184,12 @@ int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_
                         double *rate_dev, cudaStream_t st);
 // kernel ids reported in so_anneal_stats.kernel_id (names: so_kernel_name)
 enum { SO_K_NONE = 0, SO_K_TEAM = 1, SO_K_RESIDENT = 2, SO_K_GATE_INDEX = 3, SO_K_WINDOW = 4, SO_K_FLAT = 5, SO_K_GATED = 6,
-       SO_K_ANALYTICAL = 7 };
+       SO_K_ANALYTICAL = 7 };   // (the window kernel on the 24-bit packed state reports SO_K_WINDOW)
 int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int *kernel_id);
 int so_launch_islands(uint32_t *bits_dev, int64_t n, int d, int N, int W, const int32_t *index_dev, int n_strucs, int n_mutate,
                       int32_t *scratch_dev, cudaStream_t st);
+int so_launch_pack24(const int32_t *src_dev, void *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st);
+int so_launch_unpack24(const void *src_dev, int32_t *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st);
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);

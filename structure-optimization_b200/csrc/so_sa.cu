@@ -594,6 +594,13 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int
   int dev = c->lat->device, n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
+  if (s->compact) {          // 24-bit packed state: the pipelined window kernel is the only reader
+    if (!(P.variant == 0 || P.variant == 3)) {
+      so_set_error("the compact state is served by the window kernel only (variant 0 or 3, got %d)", P.variant);
+      return SO_EINVAL;
+    }
+    return kid = SO_K_WINDOW, so_launch_anneal_window(c, P, st);
+  }
   // small lattices: the whole chain state stays in shared memory for the launch (so_sa_resident.cu)
   // few chains on a small lattice: a CTA per chain (latency); many: a warp per chain (throughput)
   if ((P.variant == 0 || P.variant == 5) && so_team_ok(s, P.N, P.W, P.variant == 5 ? 1 : P.n_chains, n_sm))

@@ -36,15 +36,24 @@ __device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_
 // (profiles/r02_commit_ab.txt): at accept fractions 0.93 / 0.54 / 0.21 the TMA store takes 954 / 711 / 521 ms per sweep,
 // the register store 1001 / 769 / 576 ms, with or without the fence -- the write path is not latency bound, the nine
 // STG.128 + address arithmetic per accepted flip cost more issue slots than one UTMASTG.
-template <int HP4, int NSLOTS, int COMMIT>
+//
+// PACKED (so_surrogate_create_compact): the state is stored as 24-bit biased values, u = hq + bias_j in [0, 2^24) with
+// bias_j = -(smallest reachable hq of unit j) (the whole 24 bits cover the unit's L1 range, the intercept costs nothing), five
+// to an int4 (15 bytes + 1 pad): a site of 20 hidden units is FOUR int4 = 64 bytes instead of 80.  Records are then aligned
+// with the 64-byte L2 fill granule (the 1.13 x over-fetch of the 80-byte record disappears, profiles/
+// r02_l2_fetch_granularity.txt) and a flip moves 3,136 instead of 3,920 bytes.  Same integers, same decisions: the first
+// layer sits on a grid ~2^6 coarser (sum_k |W1q_kj| < 2^24), which the oracle mirrors (oracle/surrogate.py quantize(bits='packed24')).
+// A lane owns int4 slots q = lane + 32*it: site q >> 2, part q & 3 = lane & 3 -> hidden units 5*part .. 5*part+4.
+template <int HP4, int NSLOTS, int COMMIT, bool PACKED>
 __global__ void __launch_bounds__(WARPS * 32, 2)
     sa_window_kernel(SaParams P, WinGeom g, const int4 *__restrict__ Wst, const __grid_constant__ CUtensorMap tmap) {
   constexpr int STAGES = 3;
-  // lanes 0..STRIDE-1 own int4 slots q = lane + STRIDE*it, it < NSLOTS; STRIDE is a multiple of HP4, so a lane always
-  // sees the same hidden-unit quad and its four second-layer weights live in registers
-  constexpr int STRIDE = (32 / HP4) * HP4;
+  constexpr int SI4 = PACKED ? 4 : HP4;           // int4 per site in memory
+  // lanes 0..STRIDE-1 own int4 slots q = lane + STRIDE*it, it < NSLOTS; STRIDE is a multiple of SI4, so a lane always
+  // sees the same hidden units and its second-layer weights live in registers
+  constexpr int STRIDE = (32 / SI4) * SI4;
   extern __shared__ __align__(128) unsigned char s_raw[];
-  const int Q = P.sv.K * HP4;                     // int4 per window
+  const int Q = P.sv.K * SI4;                     // int4 per window
   const int stage_i4 = g.stage_i4;                // window + zero-weight padding, multiple of 8 int4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d;
@@ -53,15 +62,31 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
   int4 *s_Wp = (int4 *)s_raw + (size_t)WARPS * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + stage_i4;
   int4 *s_w2 = s_Wn + stage_i4;
+  // PACKED: the fifth weight of every slot, + and - tables, after the per-warp words (stage_i4 ints each)
   uint32_t *s_bits = (uint32_t *)(s_w2 + 8) + (size_t)warp * P.W;
   unsigned long long *s_bar =
       (unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) + warp * STAGES;
+  int *s_W5p = (int *)((unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) + WARPS * STAGES);
+  int *s_W5n = s_W5p + stage_i4;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   // (entries beyond the window are zero: the clamped last slot and the padding contribute exactly 0)
-  for (int q = threadIdx.x; q < stage_i4; q += blockDim.x) {
-    int4 w = q < Q ? Wst[q] : make_int4(0, 0, 0, 0);
-    s_Wp[q] = w;
-    s_Wn[q] = make_int4(-w.x, -w.y, -w.z, -w.w);
+  if constexpr (PACKED) {
+    // Wst = [Q slots][8 int32]: the five first-layer weights of the slot's hidden units, then padding
+    for (int q = threadIdx.x; q < stage_i4; q += blockDim.x) {
+      int4 w = make_int4(0, 0, 0, 0);
+      int w5 = 0;
+      if (q < Q) { w = Wst[2 * q]; w5 = Wst[2 * q + 1].x; }
+      s_Wp[q] = w;
+      s_Wn[q] = make_int4(-w.x, -w.y, -w.z, -w.w);
+      s_W5p[q] = w5;
+      s_W5n[q] = -w5;
+    }
+  } else {
+    for (int q = threadIdx.x; q < stage_i4; q += blockDim.x) {
+      int4 w = q < Q ? Wst[q] : make_int4(0, 0, 0, 0);
+      s_Wp[q] = w;
+      s_Wn[q] = make_int4(-w.x, -w.y, -w.z, -w.w);
+    }
   }
   if (lane == 0)
     for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(s_bar + i), 1);
@@ -72,7 +97,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
   // NSLOTS == 0: generic instantiation (slot count from the geometry, loops not unrolled) for shapes other than the
   // 7x7 / 20-unit headline shape
   const int nslots = NSLOTS ? NSLOTS : g.nslots;
-  const int4 w2 = lane < STRIDE ? s_w2[lane % HP4] : make_int4(0, 0, 0, 0);   // idle lanes re-read data with weight 0
+  const int4 w2 = PACKED ? make_int4(P.sv.w2q[5 * (lane & 3)], P.sv.w2q[5 * (lane & 3) + 1], P.sv.w2q[5 * (lane & 3) + 2],
+                                     P.sv.w2q[5 * (lane & 3) + 3])
+                         : (lane < STRIDE ? s_w2[lane % HP4] : make_int4(0, 0, 0, 0));   // idle lanes re-read data with weight 0
+  const int w2_5 = PACKED ? P.sv.w2q[5 * (lane & 3) + 4] : 0;
+  // PACKED: stored value u = hq + bias_j with bias_j = -(smallest reachable hq of unit j), so relu(hq) = max(u, bias_j) - bias_j
+  int B0 = 0, B1 = 0, B2 = 0, B3 = 0, B4 = 0;
+  if constexpr (PACKED) {
+    const int32_t *bs = P.sv.bias24 + 5 * (lane & 3);
+    B0 = bs[0]; B1 = bs[1]; B2 = bs[2]; B3 = bs[3]; B4 = bs[4];
+  }
   // every slot but the last stays inside the padded stage; the last one is clamped onto a zero-weight padding entry
   const int last_off = min(lane + STRIDE * (nslots - 1), stage_i4 - 1) - lane;
   const uint32_t stage_bytes = (uint32_t)Q * 16, stage_pitch = (uint32_t)stage_i4 * 16;
@@ -91,7 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     if (c >= P.n_chains) break;
     uint32_t *bits_g = P.bits + c * P.W;
     for (int w = lane; w < P.W; w += 32) s_bits[w] = bits_g[w];
-    int4 *hq = (int4 *)P.hq + c * (long long)P.N * HP4;
+    int4 *hq = (int4 *)P.hq + c * (long long)P.N * SI4;
     long long hi = P.hi[c], lo = P.lo[c];
     const double tsc = P.tscale[c];
     const float tsc_f = (float)tsc;
@@ -134,9 +168,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
           const bool interior = use_tma && q1 - gb1 >= 0 && q1 - gb1 + gL <= d && q2 - gb2 >= 0 && q2 - gb2 + gseg <= d;
           if (lane == 0) {
             mbar_expect_tx(bar, stage_bytes);
-            if (interior) tma_load_3d(dst, &tmap, (q1 - gb1) * (HP4 * 4), q2 - gb2, (int)c, bar);
+            if (interior) tma_load_3d(dst, &tmap, (q1 - gb1) * (SI4 * 4), q2 - gb2, (int)c, bar);
           }
-          if (!interior) boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, HP4, lane);   // warp-uniform
+          if (!interior) boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, SI4, lane);   // warp-uniform
         }
       }
       // ---- 2. step s ---------------------------------------------------------------------------------------
@@ -160,24 +194,50 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
             pend_f = -1;
             __syncwarp();
           }
-          reload_window_cold(stg - lane, hq, f1, f2, gb1, gb2, gL, Q, d, HP4, lane);
+          reload_window_cold(stg - lane, hq, f1, f2, gb1, gb2, gL, Q, d, SI4, lane);
           __syncwarp();
         }
         // delta-sum: D_j = sum over this lane's slots of relu(h + dw) - relu(h), dw = +-W (table chosen by the flip
         // direction).  |D_j| <= sum_k |W1q[k][j]| < 2^31 by construction of the fixed-point grid, so int32 is exact.
         const int4 *Wl = (xbit ? s_Wn : s_Wp) + lane;
         int Dx = 0, Dy = 0, Dz = 0, Dw = 0;
+        long long acc;
+        if constexpr (PACKED) {
+          const int *W5 = (xbit ? s_W5n : s_W5p) + lane;
+          int Dv = 0;
 #pragma unroll
-        for (int it = 0; it < nslots; ++it) {
-          const int off = (it == nslots - 1) ? last_off : STRIDE * it;
-          const int4 h = stg[off];
-          const int4 w = Wl[off];
-          Dx += max(h.x + w.x, 0) - max(h.x, 0);
-          Dy += max(h.y + w.y, 0) - max(h.y, 0);
-          Dz += max(h.z + w.z, 0) - max(h.z, 0);
-          Dw += max(h.w + w.w, 0) - max(h.w, 0);
+          for (int it = 0; it < nslots; ++it) {
+            const int off = (it == nslots - 1) ? last_off : STRIDE * it;
+            const int4 h = stg[off];
+            const int4 w = Wl[off];
+            const int w5 = W5[off];
+            // five 24-bit biased values in 15 bytes; relu(hq) = max(u, bias) - bias, the bias cancels in the difference
+            const int v0 = h.x & 0xffffff;
+            const int v1 = (int)(__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu);
+            const int v2 = (int)(__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu);
+            const int v3 = (int)((unsigned)h.z >> 8);
+            const int v4 = h.w & 0xffffff;
+            Dx += max(v0 + w.x, B0) - max(v0, B0);
+            Dy += max(v1 + w.y, B1) - max(v1, B1);
+            Dz += max(v2 + w.z, B2) - max(v2, B2);
+            Dw += max(v3 + w.w, B3) - max(v3, B3);
+            Dv += max(v4 + w5, B4) - max(v4, B4);
+          }
+          acc = (long long)w2.x * Dx + (long long)w2.y * Dy + (long long)w2.z * Dz + (long long)w2.w * Dw +
+                (long long)w2_5 * Dv;
+        } else {
+#pragma unroll
+          for (int it = 0; it < nslots; ++it) {
+            const int off = (it == nslots - 1) ? last_off : STRIDE * it;
+            const int4 h = stg[off];
+            const int4 w = Wl[off];
+            Dx += max(h.x + w.x, 0) - max(h.x, 0);
+            Dy += max(h.y + w.y, 0) - max(h.y, 0);
+            Dz += max(h.z + w.z, 0) - max(h.z, 0);
+            Dw += max(h.w + w.w, 0) - max(h.w, 0);
+          }
+          acc = (long long)w2.x * Dx + (long long)w2.y * Dy + (long long)w2.z * Dz + (long long)w2.w * Dw;
         }
-        long long acc = (long long)w2.x * Dx + (long long)w2.y * Dy + (long long)w2.z * Dz + (long long)w2.w * Dw;
         // exact warp sum of int64 via three 21-bit limbs (each limb sum fits 32 bits)
         {
           int l0 = (int)(acc & 0x1fffff), l1 = (int)((acc >> 21) & 0x1fffff), l2 = (int)(acc >> 42);
@@ -216,7 +276,20 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
               if (lane < STRIDE && q < Q) {
                 int4 h = stg[STRIDE * it];
                 const int4 w = Wl[STRIDE * it];
-                h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
+                if constexpr (PACKED) {
+                  const int w5 = ((xbit ? s_W5n : s_W5p) + lane)[STRIDE * it];
+                  const unsigned v0 = (unsigned)((h.x & 0xffffff) + w.x);
+                  const unsigned v1 = (__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu) + (unsigned)w.y;
+                  const unsigned v2 = (__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu) + (unsigned)w.z;
+                  const unsigned v3 = ((unsigned)h.z >> 8) + (unsigned)w.w;
+                  const unsigned v4 = (unsigned)((h.w & 0xffffff) + w5);
+                  h.x = (int)(v0 | (v1 << 24));
+                  h.y = (int)((v1 >> 8) | (v2 << 16));
+                  h.z = (int)((v2 >> 16) | (v3 << 8));
+                  h.w = (int)v4;
+                } else {
+                  h.x += w.x; h.y += w.y; h.z += w.z; h.w += w.w;
+                }
                 stg[STRIDE * it] = h;
               }
             }
@@ -227,9 +300,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
               const uint32_t src = stage0 + slot * stage_pitch;
               const bool interior = use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d;
               if (interior) {
-                if (lane == 0) tma_store_3d(&tmap, (f1 - gb1) * (HP4 * 4), f2 - gb2, (int)c, src);
+                if (lane == 0) tma_store_3d(&tmap, (f1 - gb1) * (SI4 * 4), f2 - gb2, (int)c, src);
               } else {
-                boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, HP4, lane);     // warp-uniform branch
+                boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, SI4, lane);     // warp-uniform branch
               }
               if (lane == 0 || !interior) {
                 bulk_commit();
@@ -291,22 +364,67 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
   }
 }
 
-}  // namespace
-
 static int window_stage_i4(int Q) { return (Q + 3 + 7) & ~7; }
 
-size_t so_window_smem_bytes(int Q, int W, int stages) {
+static size_t window_smem_bytes(int Q, int W, int stages) {
   size_t st_i4 = window_stage_i4(Q);
   size_t i4 = 8 + 2 * st_i4 + (size_t)WARPS * stages * st_i4;
   size_t words = ((size_t)WARPS * W + 3) & ~(size_t)3;
-  return i4 * 16 + words * 4 + (size_t)WARPS * stages * 8 + 16;
+  return i4 * 16 + words * 4 + (size_t)WARPS * stages * 8 + 16 + 2 * st_i4 * 4;   // (+ the fifth-weight tables of PACKED)
 }
 
-template <int HP4, int NSLOTS, int COMMIT>
+// int32 state [sites][20] -> 24-bit biased, five values per int4, four int4 (64 bytes) per site
+__global__ void pack24_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, long long n_sites,
+                              const int32_t *__restrict__ bias) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_sites * 4) return;
+  const long long site = t >> 2;
+  const int part = (int)(t & 3);
+  const int *h = (const int *)(src + site * 5) + 5 * part;
+  const int32_t *b = bias + 5 * part;
+  const unsigned v0 = (unsigned)(h[0] + b[0]) & 0xffffffu, v1 = (unsigned)(h[1] + b[1]) & 0xffffffu,
+                 v2 = (unsigned)(h[2] + b[2]) & 0xffffffu, v3 = (unsigned)(h[3] + b[3]) & 0xffffffu,
+                 v4 = (unsigned)(h[4] + b[4]) & 0xffffffu;
+  dst[t] = make_int4((int)(v0 | (v1 << 24)), (int)((v1 >> 8) | (v2 << 16)), (int)((v2 >> 16) | (v3 << 8)), (int)v4);
+}
+__global__ void unpack24_kernel(const int4 *__restrict__ src, int *__restrict__ dst, long long n_sites,
+                                const int32_t *__restrict__ bias) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_sites * 4) return;
+  const int4 h = src[t];
+  int *o = dst + (t >> 2) * 20 + 5 * (int)(t & 3);
+  const int32_t *b = bias + 5 * (int)(t & 3);
+  o[0] = (int)((unsigned)h.x & 0xffffffu) - b[0];
+  o[1] = (int)(__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu) - b[1];
+  o[2] = (int)(__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu) - b[2];
+  o[3] = (int)((unsigned)h.z >> 8) - b[3];
+  o[4] = (int)((unsigned)h.w & 0xffffffu) - b[4];
+}
+
+}  // namespace
+
+size_t so_window_smem_bytes(int Q, int W, int stages) { return window_smem_bytes(Q, W, stages); }
+
+int so_launch_pack24(const int32_t *src_dev, void *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st) {
+  if (n_sites == 0) return SO_OK;
+  pack24_kernel<<<(unsigned)((n_sites * 4 + 255) / 256), 256, 0, st>>>((const int4 *)src_dev, (int4 *)dst_dev, n_sites, bias_dev);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+int so_launch_unpack24(const void *src_dev, int32_t *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st) {
+  if (n_sites == 0) return SO_OK;
+  unpack24_kernel<<<(unsigned)((n_sites * 4 + 255) / 256), 256, 0, st>>>((const int4 *)src_dev, dst_dev, n_sites, bias_dev);
+  SO_CUDA(cudaGetLastError());
+  return SO_OK;
+}
+
+namespace {
+
+template <int HP4, int NSLOTS, int COMMIT, bool PACKED>
 static int launch_window(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks, cudaStream_t st) {
-  auto kern = sa_window_kernel<HP4, NSLOTS, COMMIT>;
+  auto kern = sa_window_kernel<HP4, NSLOTS, COMMIT, PACKED>;
   SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)c->sur->Wst_dev, c->tmap);
+  kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)(PACKED ? c->sur->Wst24_dev : c->sur->Wst_dev), c->tmap);
   SO_CUDA(cudaGetLastError());
   return SO_OK;
 }
@@ -325,9 +443,9 @@ template <int HP4, int NSLOTS>
 static int launch_window_commit(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks,
                                 cudaStream_t st) {
   switch (window_commit_mode()) {
-    case 2: return launch_window<HP4, NSLOTS, 2>(c, P, g, smem, blocks, st);
-    case 1: return launch_window<HP4, NSLOTS, 1>(c, P, g, smem, blocks, st);
-    default: return launch_window<HP4, NSLOTS, 0>(c, P, g, smem, blocks, st);
+    case 2: return launch_window<HP4, NSLOTS, 2, false>(c, P, g, smem, blocks, st);
+    case 1: return launch_window<HP4, NSLOTS, 1, false>(c, P, g, smem, blocks, st);
+    default: return launch_window<HP4, NSLOTS, 0, false>(c, P, g, smem, blocks, st);
   }
 }
 
@@ -338,8 +456,10 @@ static int launch_window_hp4(const so_chains *c, const SaParams &P, const WinGeo
                              cudaStream_t st) {
   if (g.nslots > 10) { so_set_error("window too large for the pipelined kernel"); return SO_EINVAL; }
   if (HP4 == 5 && g.nslots == 9) return launch_window_commit<5, 9>(c, P, g, smem, blocks, st);
-  return launch_window<HP4, 0, 0>(c, P, g, smem, blocks, st);
+  return launch_window<HP4, 0, 0, false>(c, P, g, smem, blocks, st);
 }
+
+}  // namespace
 
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st) {
   const so_surrogate *s = c->sur;
@@ -348,14 +468,23 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
   WinGeom g;
   g.b1 = s->win_b1; g.b2 = s->win_b2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
   g.use_tma = c->tmap_ok;
+  long long want = (P.n_chains + WARPS - 1) / WARPS;
+  int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
+  if (blocks < 1) blocks = 1;
+  if (s->compact) {                              // 24-bit packed state: 4 int4 per site, all 32 lanes own slots
+    const int Q = s->K * 4;
+    g.stage_i4 = window_stage_i4(Q);
+    g.nslots = (Q + 31) / 32;
+    if (g.nslots > 10) { so_set_error("window too large for the pipelined kernel"); return SO_EINVAL; }
+    const size_t smem = so_window_smem_bytes(Q, P.W, 3);
+    if (g.nslots == 7) return launch_window<5, 7, 0, true>(c, P, g, smem, blocks, st);
+    return launch_window<5, 0, 0, true>(c, P, g, smem, blocks, st);
+  }
   const int Q = s->K * s->HP4;
   const int stride = (32 / s->HP4) * s->HP4;
   g.stage_i4 = window_stage_i4(Q);
   g.nslots = (Q + stride - 1) / stride;
   size_t smem = so_window_smem_bytes(Q, P.W, 3);
-  long long want = (P.n_chains + WARPS - 1) / WARPS;
-  int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
-  if (blocks < 1) blocks = 1;
   switch (s->HP4) {
     case 1: return launch_window_hp4<1>(c, P, g, smem, blocks, st);
     case 2: return launch_window_hp4<2>(c, P, g, smem, blocks, st);

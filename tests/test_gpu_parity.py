@@ -555,6 +555,70 @@ def test_type_histograms_tracked_inside_the_sa_step(eng, d, descriptor, gated, v
         ch.type_histograms()
 
 
+@pytest.mark.parametrize("d,n,steps,T0", [(7, 40, 600, 2.0), (12, 300, 800, 1.5), (20, 300, 600, 1.0), (96, 64, 1200, 1.0)])
+def test_compact_state_window_kernel(eng, d, n, steps, T0):
+    """24-bit packed first-layer state (so_surrogate_create_compact, 64 bytes per site): the window kernel on it takes the
+    decisions of the exact integer arithmetic on the coarser grid -- oracle.quantize(bits='packed24') -- bit for bit: accept
+    vectors, occupancies, exact sums, the whole unpacked state; scores within the 1e-5 bar of the fp64 surrogate; hot chains
+    (boundary-crossing and stale windows everywhere on the small lattices)."""
+    from oracle import c_oracle
+    N = d * d
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=21, y_mean=0.1, y_scale=1.7)
+    q = S.quantize(p, bits="packed24")
+    lat = eng.Lattice(d, "NH3")
+    tab = eng.SurrogateTables(lat, p.offsets, p.W1, p.b1, p.w2, p.b2, p.y_mean, p.y_scale, compact=True)
+    assert tab.e_h == q["e_h"] and tab.e_w == q["e_w"]
+    rng = np.random.default_rng(d)
+    x0 = (rng.random((n, N)) < 0.5).astype(np.uint8)
+    prop = rng.integers(0, N, (n, steps)).astype(np.int32)
+    u = rng.random((n, steps), dtype=np.float32)
+    temps = SA.schedule("exp", T0, steps)
+    ch = eng.Chains(lat, n)
+    ch.set_occupancy(x0)
+    ch.attach(tab)
+    hq0, _ = S.preact_fixed(p, q, x0[3], d)
+    assert (ch.preact(3)[:, :20] == hq0[:, :20]).all()                   # pack / unpack round trip of the state build
+    for c in range(0, n, max(1, n // 8)):
+        ref = S.eval_rate_fp64(p, L.descriptor_rows(x0[c], p.offsets, d))
+        assert abs(ch.objective(c, 1)[0] - ref) <= 1e-5 * max(abs(ref), 1e-12)
+    ch.track_types(True)
+    st, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True)
+    assert st["kernel"] == "sa_window_kernel" and st["accepted"] > 0.05 * st["flips"]
+    o = c_oracle.anneal_fixed_many(p, q, d, x0, temps, prop, u)
+    assert (acc.astype(bool) == o["accept"]).all()
+    x1 = ch.get_occupancy()
+    assert (x1 == o["x"]).all()
+    of, hi, lo, na = ch.objective(sums=True)
+    assert (hi == o["hi"]).all() and (lo == o["lo"]).all() and (of == o["OF"]).all()
+    hq1, _ = S.preact_fixed(p, q, x1[5], d)
+    assert (ch.preact(5)[:, :20] == hq1[:, :20]).all()                   # every accepted update landed, repacked exactly
+    assert (ch.score() == of).all()                                      # tracked sums == fresh recompute
+    lh, ne = ch.type_histograms()
+    assert (ne == ST.nh3_export_hist(ST.nh3_types(x1, d))).all()
+    # the same steps in three launches (resume) and from Philox draws twice (determinism)
+    ch.set_occupancy(x0)
+    for a, b in ((0, 100), (100, 101), (101, steps)):
+        ch.anneal(temps[a:b], step0=a, proposals=prop[:, a:b], uniforms=u[:, a:b])
+    assert (ch.get_occupancy() == x1).all()
+    ch.set_occupancy(x0)
+    ch.anneal(temps, seed=3)
+    xa = ch.get_occupancy()
+    ch.set_occupancy(x0)
+    ch.anneal(temps, seed=3)
+    assert (ch.get_occupancy() == xa).all()
+    with pytest.raises(ValueError):
+        ch.anneal(temps[:10], seed=3, variant=2)                         # the generic kernels read the int32 layout
+    with pytest.raises(ValueError):
+        eng.SurrogateTables(lat, p.offsets, p.W1[:, :8], p.b1[:8], p.w2[:8], p.b2, compact=True)
+    # near ties are re-decided from the fp64 weights: decisions equal the fp64 rule
+    ch.set_occupancy(x0)
+    tol = 8.0 * np.sqrt(tab.K) * np.ldexp(1.0, tab.e_h) * abs(p.y_scale) * float(np.abs(p.w2).sum())
+    _, acc2 = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True, exact_guard=True, guard_tol=tol)
+    o64 = c_oracle.anneal_fp64_many(p, d, x0, temps, prop, u, margin_thr=1e-9)
+    ok = o64["n_below"] == 0
+    assert (acc2.astype(bool)[ok] == o64["accept"][ok]).all() and ok.mean() > 0.95
+
+
 def test_checkpoint_resume_is_bit_exact(eng, tmp_path):
     """so_chains_save / so_chains_load: a run cut at a checkpoint and resumed in a NEW handle ends with the same bits,
     sums and temperatures as the uninterrupted run (counter-based draws; the state is an exact function of the bits)."""
