@@ -18,7 +18,7 @@ rt.cudaDeviceGetLimit(ctypes.byref(val), 7)          # cudaLimitMaxL2FetchGranul
 print("cudaLimitMaxL2FetchGranularity reads back as", val.value)
 off = engine.local_offsets(3)
 W1, b1, w2, b2 = bench.glorot_mlp(off, bench.H, 0)
-tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2)
+tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, compact=os.environ.get('SO_COMPACT', '1') != '0')
 ch = engine.Chains(lat, chains)
 ch.randomize(seed=1234, coverage=0.5)
 ch.attach(tab)

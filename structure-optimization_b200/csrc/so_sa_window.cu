@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 8;          // warps (= chains in flight) per CTA of the int32-state kernel; the packed one may take more
 
 // slow, exact side of the Metropolis rule for one step; reloads the fp64 temperature.  bit 0 accept, bit 1 guard
 __device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_c, double tsc, const double *temps,
@@ -44,8 +44,8 @@ __device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_
 // r02_l2_fetch_granularity.txt) and a flip moves 3,136 instead of 3,920 bytes.  Same integers, same decisions: the first
 // layer sits on a grid ~2^6 coarser (sum_k |W1q_kj| < 2^24), which the oracle mirrors (oracle/surrogate.py quantize(bits='packed24')).
 // A lane owns int4 slots q = lane + 32*it: site q >> 2, part q & 3 = lane & 3 -> hidden units 5*part .. 5*part+4.
-template <int HP4, int NSLOTS, int COMMIT, bool PACKED>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <int HP4, int NSLOTS, int COMMIT, bool PACKED, int NW = WARPS>
+__global__ void __launch_bounds__(NW * 32, 2)
     sa_window_kernel(SaParams P, WinGeom g, const int4 *__restrict__ Wst, const __grid_constant__ CUtensorMap tmap) {
   constexpr int STAGES = 3;
   constexpr int SI4 = PACKED ? 4 : HP4;           // int4 per site in memory
@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
   const int d = P.d;
   // shared layout: [per warp: STAGES stages][+W: stage_i4][-W: stage_i4][w2: 8 int4][per warp: bits][per warp: mbarriers]
   int4 *s_stage = (int4 *)s_raw + (size_t)warp * STAGES * stage_i4;
-  int4 *s_Wp = (int4 *)s_raw + (size_t)WARPS * STAGES * stage_i4;
+  int4 *s_Wp = (int4 *)s_raw + (size_t)NW * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + stage_i4;
   int4 *s_w2 = s_Wn + stage_i4;
   // PACKED: the fifth weight of every slot, + and - tables, after the per-warp words (stage_i4 ints each)
   uint32_t *s_bits = (uint32_t *)(s_w2 + 8) + (size_t)warp * P.W;
   unsigned long long *s_bar =
-      (unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) + warp * STAGES;
-  int *s_W5p = (int *)((unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)WARPS * P.W + 3) & ~(size_t)3)) + WARPS * STAGES);
+      (unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * P.W + 3) & ~(size_t)3)) + warp * STAGES;
+  int *s_W5p = (int *)((unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * P.W + 3) & ~(size_t)3)) + NW * STAGES);
   int *s_W5n = s_W5p + stage_i4;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   // (entries beyond the window are zero: the clamped last slot and the padding contribute exactly 0)
@@ -366,11 +366,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 
 static int window_stage_i4(int Q) { return (Q + 3 + 7) & ~7; }
 
-static size_t window_smem_bytes(int Q, int W, int stages) {
+static size_t window_smem_bytes(int Q, int W, int stages, int nw = WARPS) {
   size_t st_i4 = window_stage_i4(Q);
-  size_t i4 = 8 + 2 * st_i4 + (size_t)WARPS * stages * st_i4;
-  size_t words = ((size_t)WARPS * W + 3) & ~(size_t)3;
-  return i4 * 16 + words * 4 + (size_t)WARPS * stages * 8 + 16 + 2 * st_i4 * 4;   // (+ the fifth-weight tables of PACKED)
+  size_t i4 = 8 + 2 * st_i4 + (size_t)nw * stages * st_i4;
+  size_t words = ((size_t)nw * W + 3) & ~(size_t)3;
+  return i4 * 16 + words * 4 + (size_t)nw * stages * 8 + 16 + 2 * st_i4 * 4;   // (+ the fifth-weight tables of PACKED)
 }
 
 // int32 state [sites][20] -> 24-bit biased, five values per int4, four int4 (64 bytes) per site
@@ -420,11 +420,11 @@ int so_launch_unpack24(const void *src_dev, int32_t *dst_dev, int64_t n_sites, c
 
 namespace {
 
-template <int HP4, int NSLOTS, int COMMIT, bool PACKED>
+template <int HP4, int NSLOTS, int COMMIT, bool PACKED, int NW = WARPS>
 static int launch_window(const so_chains *c, const SaParams &P, const WinGeom &g, size_t smem, int blocks, cudaStream_t st) {
-  auto kern = sa_window_kernel<HP4, NSLOTS, COMMIT, PACKED>;
+  auto kern = sa_window_kernel<HP4, NSLOTS, COMMIT, PACKED, NW>;
   SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, WARPS * 32, smem, st>>>(P, g, (const int4 *)(PACKED ? c->sur->Wst24_dev : c->sur->Wst_dev), c->tmap);
+  kern<<<blocks, NW * 32, smem, st>>>(P, g, (const int4 *)(PACKED ? c->sur->Wst24_dev : c->sur->Wst_dev), c->tmap);
   SO_CUDA(cudaGetLastError());
   return SO_OK;
 }
@@ -476,9 +476,10 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
     g.stage_i4 = window_stage_i4(Q);
     g.nslots = (Q + 31) / 32;
     if (g.nslots > 10) { so_set_error("window too large for the pipelined kernel"); return SO_EINVAL; }
-    const size_t smem = so_window_smem_bytes(Q, P.W, 3);
-    if (g.nslots == 7) return launch_window<5, 7, 0, true>(c, P, g, smem, blocks, st);
-    return launch_window<5, 0, 0, true>(c, P, g, smem, blocks, st);
+    // (10 or 12 warps per CTA fit the smaller packed stages, but at 96 / 80 registers per thread the spills cost more than
+    // the extra warps hide: 1.44e9 -> 1.12e9 flip-evaluations/s on one box)
+    if (g.nslots == 7) return launch_window<5, 7, 0, true>(c, P, g, window_smem_bytes(Q, P.W, 3), blocks, st);
+    return launch_window<5, 0, 0, true>(c, P, g, window_smem_bytes(Q, P.W, 3), blocks, st);
   }
   const int Q = s->K * s->HP4;
   const int stride = (32 / s->HP4) * s->HP4;
