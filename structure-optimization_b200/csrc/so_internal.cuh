@@ -255,6 +255,14 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SO_FULL, v); }
 
+// ONE near-tie predicate for every SA kernel (exact_guard): the rule is "accept iff delta > thr" with thr = T ln u for
+// T > 0 and u > 0 (no finite threshold for u = 0), thr = 0 for T <= 0; a decision is re-taken from the fp64 weights when
+// the quantised delta is within tol of thr -- whatever its sign.
+__device__ __forceinline__ bool so_near_tie(double delta, double T, float u, double tol) {
+  if (T > 0.0) return u > 0.f && fabs(delta - T * log((double)u)) < tol;
+  return fabs(delta) < tol;
+}
+
 // ---- tree gate ----------------------------------------------------------------------------------------
 // Descriptor column c of row (r1,r2) is the site (r1+o1[c], r2+o2[c]).
 // gate of row (r1,r2) before and after flipping site f in ONE walk: both walks share the path until a node tests the

@@ -157,14 +157,7 @@ __device__ __forceinline__ bool metropolis(double delta, double T, float u, doub
   if (delta > 0.0) acc = true;
   else if (T > 0.0) acc = exp(delta / T) > (double)u;
   else acc = false;
-  guard = false;
-  if (tol > 0.0) {
-    if (T > 0.0) {
-      if (u > 0.0f) guard = fabs(delta - T * log((double)u)) < tol;
-    } else {
-      guard = fabs(delta) < tol;
-    }
-  }
+  guard = tol > 0.0 && so_near_tie(delta, T, u, tol);
   return acc;
 }
 

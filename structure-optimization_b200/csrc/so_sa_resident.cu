@@ -61,17 +61,11 @@ __device__ __noinline__ DrawR draw_batch_res(const double *temps, const int32_t 
 __device__ __noinline__ int decide_res(double delta, double tsc, const double *temps, long long s, float u, int exact_guard,
                                        double tol) {
   const double T = __dmul_rn(tsc, __ldg(temps + s));
-  bool accept, guard = false;
-  if (delta > 0.0) {
-    accept = true;
-    if (exact_guard && T <= 0.0 && delta < tol) guard = true;
-  } else if (T > 0.0) {
-    accept = exp(delta / T) > (double)u;
-    if (exact_guard && u > 0.f) guard = fabs(delta - T * log((double)u)) < tol;
-  } else {
-    accept = false;
-    if (exact_guard && delta > -tol) guard = true;
-  }
+  bool accept;
+  if (delta > 0.0) accept = true;
+  else if (T > 0.0) accept = exp(delta / T) > (double)u;
+  else accept = false;
+  const bool guard = exact_guard && so_near_tie(delta, T, u, tol);
   return (accept ? 1 : 0) | (guard ? 2 : 0);
 }
 __device__ __noinline__ int exact_decision_res(const SurView sv, const uint32_t *bits, int d, int f, int lane, double tsc,
@@ -451,7 +445,7 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
         // fp32 pre-filter: decides when p = exp(delta/T) is at least 1e-3 (relative) away from u; with the exact guard
         // on, only where that margin also rules out |delta - T ln u| < tol  (the margin means |ln p - ln u| > 9.8e-4, so tol / T < 5e-4 is safe)
         const float pf = __expf(__fdividef((float)delta, Tf));
-        if (delta > 0.0 && (Tf > 0.f || !guard_on)) {
+        if (delta > 0.0 && (!guard_on || delta >= P.guard_tol)) {     // (with the guard: only when no tie is possible)
           accept = true;
         } else if (delta <= 0.0 && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u) &&
                    (!guard_on || tol_f < 5e-4f * Tf)) {
@@ -748,7 +742,7 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32) sa_team_kernel(SaParams P) {
       bool accept;
       {
         const float pf = __expf(__fdividef((float)delta, Tf));
-        if (delta > 0.0 && (Tf > 0.f || !guard_on)) {
+        if (delta > 0.0 && (!guard_on || delta >= P.guard_tol)) {     // (with the guard: only when no tie is possible)
           accept = true;
         } else if (delta <= 0.0 && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u) &&
                    (!guard_on || tol_f < 5e-4f * Tf)) {

@@ -104,17 +104,11 @@ __device__ __noinline__ Draw draw_batch_cold(const double *temps, const int32_t 
 
 // the fp64 Metropolis rule (OML/optimize_SA.py:108-116) + the near-tie guard; bit 0 = accept, bit 1 = guard
 __device__ __noinline__ int metropolis_cold(double delta, double T, float u, int exact_guard, double tol) {
-  bool accept, guard = false;
-  if (delta > 0.0) {
-    accept = true;
-    if (exact_guard && T <= 0.0 && delta < tol) guard = true;
-  } else if (T > 0.0) {
-    accept = exp(delta / T) > (double)u;
-    if (exact_guard && u > 0.f) guard = fabs(delta - T * log((double)u)) < tol;
-  } else {
-    accept = false;
-    if (exact_guard && delta > -tol) guard = true;
-  }
+  bool accept;
+  if (delta > 0.0) accept = true;
+  else if (T > 0.0) accept = exp(delta / T) > (double)u;
+  else accept = false;
+  const bool guard = exact_guard && so_near_tie(delta, T, u, tol);
   return (accept ? 1 : 0) | (guard ? 2 : 0);
 }
 

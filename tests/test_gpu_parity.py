@@ -619,6 +619,38 @@ def test_compact_state_window_kernel(eng, d, n, steps, T0):
     assert (acc2.astype(bool)[ok] == o64["accept"][ok]).all() and ok.mean() > 0.95
 
 
+@pytest.mark.parametrize("descriptor,variants", [("full", (0, 1, 2, 3, 4, 5)), ("local", (0, 2, 3, 4))])
+def test_near_tie_guard_is_one_predicate_in_every_kernel(eng, descriptor, variants):
+    """the exact guard must fire on the same steps in every SA kernel.  With a guard tolerance larger than any
+    |delta - T ln u| EVERY decision at T > 0, u > 0 is re-taken from the fp64 weights, whatever the sign of the quantised
+    delta: guard_fired counts all of them in each kernel, and the accept vectors equal the fp64 rule's."""
+    from oracle import c_oracle
+    d, N, n, steps = 12, 144, 48, 300
+    gated = descriptor == "full"
+    p = Hp.golden_surrogate(gated=True) if gated else S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=8)
+    lat = eng.Lattice(d, "LSC")
+    tab = Hp.tables_from_params(lat, p)
+    rng = np.random.default_rng(12)
+    x0 = (rng.random((n, N)) < 0.5).astype(np.uint8)
+    prop = rng.integers(0, N, (n, steps)).astype(np.int32)
+    u = rng.random((n, steps), dtype=np.float32)
+    u[u == 0] = 0.5
+    temps = SA.schedule("exp", 0.3, steps)
+    o64 = c_oracle.anneal_fp64_many(p, d, x0, temps, prop, u, margin_thr=1e-9)
+    assert o64["n_below"].sum() == 0
+    for v in variants:
+        ch = eng.Chains(lat, n if v != 5 else 4)
+        m = ch.n
+        ch.set_occupancy(x0[:m])
+        ch.attach(tab)
+        st, acc = ch.anneal(temps, proposals=prop[:m], uniforms=u[:m], want_accept=True, exact_guard=True, guard_tol=1e30,
+                            variant=v)
+        assert st["guard_fired"] == m * steps, (v, st["kernel"], st["guard_fired"])
+        assert (acc.astype(bool) == o64["accept"][:m]).all(), (v, st["kernel"])
+        assert (ch.get_occupancy() == o64["x"][:m]).all()
+        ch.close()
+
+
 def test_checkpoint_resume_is_bit_exact(eng, tmp_path):
     """so_chains_save / so_chains_load: a run cut at a checkpoint and resumed in a NEW handle ends with the same bits,
     sums and temperatures as the uninterrupted run (counter-based draws; the state is an exact function of the bits)."""
