@@ -20,7 +20,8 @@ namespace {
 
 constexpr int WARPS = 8;          // warps (= chains in flight) per CTA of the int32-state kernel; the packed one may take more
 
-// slow, exact side of the Metropolis rule for one step; reloads the fp64 temperature.  bit 0 accept, bit 1 guard
+// slow, exact side of the Metropolis rule for one step; reloads the fp64 temperature and redraws the step's uniform (the hot
+// loop carries only the fp32 threshold).  bit 0 accept, bit 1 guard
 __device__ __noinline__ int decide_cold(long long acc, double k_sigma, double k_c, double tsc, const double *temps,
                                         long long s, float u, int exact_guard, double tol) {
   // == so_real(c, b2, sigma, mu, acc >> 20, acc & mask, 0): with n = 0 the pinned sequence reduces to
@@ -57,16 +58,16 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int stage_i4 = g.stage_i4;                // window + zero-weight padding, multiple of 8 int4
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = P.d;
-  // shared layout: [per warp: STAGES stages][+W: stage_i4][-W: stage_i4][w2: 8 int4][per warp: bits][per warp: mbarriers]
-  int4 *s_stage = (int4 *)s_raw + (size_t)warp * STAGES * stage_i4;
+  // shared layout: [per warp: STAGES stages][+W: stage_i4][-W: stage_i4][w2: 8 int4][per warp: bits][PACKED: fifth weights]
+  // The mbarrier of a stage lives INSIDE the stage, in the first zero-weight padding entry behind the window (int4 index Q):
+  // one running byte offset addresses the data and the barrier of the stage in use
+  unsigned char *s_stage = s_raw + (size_t)warp * STAGES * stage_i4 * 16;
   int4 *s_Wp = (int4 *)s_raw + (size_t)NW * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + stage_i4;
   int4 *s_w2 = s_Wn + stage_i4;
-  // PACKED: the fifth weight of every slot, + and - tables, after the per-warp words (stage_i4 ints each)
   uint32_t *s_bits = (uint32_t *)(s_w2 + 8) + (size_t)warp * P.W;
-  unsigned long long *s_bar =
-      (unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * P.W + 3) & ~(size_t)3)) + warp * STAGES;
-  int *s_W5p = (int *)((unsigned long long *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * P.W + 3) & ~(size_t)3)) + NW * STAGES);
+  // PACKED: the fifth weight of every slot, + and - tables, after the per-warp words (stage_i4 ints each)
+  int *s_W5p = (int *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * P.W + 3) & ~(size_t)3));
   int *s_W5n = s_W5p + stage_i4;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   // (entries beyond the window are zero: the clamped last slot and the padding contribute exactly 0)
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
     }
   }
   if (lane == 0)
-    for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(s_bar + i), 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(s_stage) + (uint32_t)(i * stage_i4 + Q) * 16, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_async_smem();
   __syncthreads();
@@ -109,14 +110,21 @@ __global__ void __launch_bounds__(NW * 32, 2)
   }
   // every slot but the last stays inside the padded stage; the last one is clamped onto a zero-weight padding entry
   const int last_off = min(lane + STRIDE * (nslots - 1), stage_i4 - 1) - lane;
-  const uint32_t stage_bytes = (uint32_t)Q * 16, stage_pitch = (uint32_t)stage_i4 * 16;
-  const uint32_t stage0 = smem_u32(s_stage), bar0 = smem_u32(s_bar);
-  uint32_t phase_bits = 0;                          // parity of each stage's mbarrier (bit i)
+  const uint32_t stage_bytes = (uint32_t)Q * 16, stage_pitch = (uint32_t)stage_i4 * 16, ring_bytes = STAGES * stage_pitch;
+  const uint32_t stage0 = smem_u32(s_stage);
+  // fp32 image of delta = sigma * c * acc (signed scale).  A scale that is not a normal fp32 number disables the fp32 side
   const float k_f = (float)(P.sv.y_scale * P.sv.c);
-  const bool sigma_pos = P.sv.y_scale > 0.0;
+  const int fast_ok = !P.exact_guard && fabsf(k_f) > 1e-30f && fabsf(k_f) < 1e30f;
   const int gb1 = g.b1, gb2 = g.b2, gL = g.L, gseg = g.n_seg;
-  const bool use_tma = g.use_tma != 0;
-  const bool fast_ok = !P.exact_guard;
+  // a window is interior (one tensor-TMA box) iff 0 <= f1 - b1 <= d - L and 0 <= f2 - b2 <= d - n_seg: two unsigned tests
+  const unsigned lim1 = g.use_tma ? (unsigned)(d - gL + 1) : 0u, lim2 = g.use_tma ? (unsigned)(d - gseg + 1) : 0u;
+  const int n_steps = (int)P.n_steps;               // (the launcher refuses launches of 2^31 steps or more)
+
+  // ring of stages, continuous over all chains of the warp: the k-th window the warp ever computes on sits in stage k % 3
+  // and was the k-th load issued, so its mbarrier phase has parity (k / 3) & 1.  Iteration s of a chain prefetches into
+  // the stage at byte offset p_off (the one step s-1 computed in) and computes in the next stage round the ring (c_off);
+  // par flips whenever c_off wraps.  (p_off, par) = the state after computing window k-1; start: k = -2.
+  uint32_t p_off = 0, par = 1;
 
   for (;;) {
     long long c = 0;
@@ -128,35 +136,37 @@ __global__ void __launch_bounds__(NW * 32, 2)
     int4 *hq = (int4 *)P.hq + c * (long long)P.N * SI4;
     long long hi = P.hi[c], lo = P.lo[c];
     const double tsc = P.tscale[c];
-    const float tsc_f = (float)tsc;
     unsigned n_acc = 0, n_guard = 0;
     __syncwarp();
 
     Draw batch;                                     // lane l: draws of step 32*b + l
-    batch.f = 0; batch.u = 0.f; batch.t = 0.0;
-    float batch_tf = 0.f;
+    batch.f = 0; batch.thr = 0.f;
     // pipeline registers: draws of the steps whose windows are in flight
     int f_a = 0, f_b = 0;
-    float u_a = 0.f, u_b = 0.f, t_a = 0.f, t_b = 0.f;
+    float thr_a = 0.f, thr_b = 0.f;
     int hist0 = -1, hist1 = -1;                     // flips accepted at steps s-1, s-2 (their windows were prefetched earlier)
     int pend_f = -1;                                // COMMIT == 0: flip whose TMA store may still be in flight
-    int slot = 1;                                   // stage of step s (s starts at -(STAGES-1) = -2)
-
-    for (long long s = -(STAGES - 1); s < P.n_steps; ++s) {
+    for (int s = -(STAGES - 1); s < n_steps; ++s) {
+      uint32_t c_off = p_off + stage_pitch;
+      if (c_off == ring_bytes) { c_off = 0; par ^= 1u; }
       // ---- 1. prefetch the window of step s+2 into the stage freed by step s-1 -------------------------------
-      const long long sp = s + (STAGES - 1);
+      const int sp = s + (STAGES - 1);
       int f_q = 0;
-      float u_q = 0.f, t_q = 0.f;
-      if (sp < P.n_steps) {
+      float thr_q = 0.f;
+      if (sp < n_steps) {
         if ((sp & 31) == 0) {
           batch = draw_batch_cold(P.temps, P.proposals, P.uniforms, P.n_steps, P.step0, P.chain_id0 + c, c, P.seed, P.N, d,
-                                  sp >> 5, lane);
-          batch_tf = (float)batch.t;
+                                  sp >> 5, lane, tsc, fast_ok);
+          // a store issued at least two steps ago has long landed: retire it here, once per 32 steps, so that the per-step
+          // overlap test below runs only right after an accepted flip
+          if (COMMIT == 0 && pend_f >= 0) {
+            bulk_wait_all();
+            pend_f = -1;
+            __syncwarp();
+          }
         }
-        f_q = __shfl_sync(SO_FULL, batch.f, (int)(sp & 31));
-        u_q = __shfl_sync(SO_FULL, batch.u, (int)(sp & 31));
-        t_q = __shfl_sync(SO_FULL, batch_tf, (int)(sp & 31));
-        const int pslot = slot == 0 ? STAGES - 1 : slot - 1;
+        f_q = __shfl_sync(SO_FULL, batch.f, sp & 31);
+        thr_q = __shfl_sync(SO_FULL, batch.thr, sp & 31);
         const int q1 = pk1(f_q), q2 = pk2(f_q);
         if (COMMIT == 0 && pend_f >= 0 && near_cyclic(q1, pk1(pend_f), gL - 1, d) && near_cyclic(q2, pk2(pend_f), gseg - 1, d)) {
           bulk_wait_all();                          // the store of that region may still be in flight
@@ -164,19 +174,24 @@ __global__ void __launch_bounds__(NW * 32, 2)
           __syncwarp();
         }
         {
-          const uint32_t bar = bar0 + pslot * 8, dst = stage0 + pslot * stage_pitch;
-          const bool interior = use_tma && q1 - gb1 >= 0 && q1 - gb1 + gL <= d && q2 - gb2 >= 0 && q2 - gb2 + gseg <= d;
-          if (lane == 0) {
-            mbar_expect_tx(bar, stage_bytes);
-            if (interior) tma_load_3d(dst, &tmap, (q1 - gb1) * (SI4 * 4), q2 - gb2, (int)c, bar);
+          const uint32_t dst = stage0 + p_off, bar = dst + stage_bytes;
+          const bool interior = ((unsigned)(q1 - gb1) < lim1) & ((unsigned)(q2 - gb2) < lim2);
+          if (interior) {
+            if (lane == 0) {
+              mbar_expect_tx(bar, stage_bytes);
+              tma_load_3d(dst, &tmap, (q1 - gb1) * (SI4 * 4), q2 - gb2, (int)c, bar);
+            }
+          } else {                                  // warp-uniform branch; the whole warp enters the call converged
+            if (lane == 0) mbar_expect_tx(bar, stage_bytes);
+            __syncwarp();
+            boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, SI4, lane);
           }
-          if (!interior) boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, SI4, lane);   // warp-uniform
         }
       }
       // ---- 2. step s ---------------------------------------------------------------------------------------
       if (s >= 0) {
         const int fp = f_b;
-        const float u = u_b;
+        const float thr = thr_b;
         const int f1 = pk1(fp), f2 = pk2(fp);
         const int f = f2 * d + f1;
         bool stale = false;
@@ -185,9 +200,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
           if (hist1 >= 0) stale |= near_cyclic(f1, pk1(hist1), gL - 1, d) && near_cyclic(f2, pk2(hist1), gseg - 1, d);
         }
         const int xbit = (s_bits[f >> 5] >> (f & 31)) & 1;
-        mbar_wait(bar0 + slot * 8, (phase_bits >> slot) & 1u);
-        phase_bits ^= (1u << slot);
-        int4 *stg = s_stage + slot * stage_i4 + lane;
+        mbar_wait(stage0 + c_off + stage_bytes, par);
+        int4 *stg = (int4 *)(s_stage + c_off) + lane;
         if (stale) {                                // the writers' stores are ordered before this by their __syncwarp
           if (COMMIT == 0) {
             bulk_wait_all();                        // every lane: the stores it issued are complete and visible
@@ -211,12 +225,13 @@ __global__ void __launch_bounds__(NW * 32, 2)
             const int4 h = stg[off];
             const int4 w = Wl[off];
             const int w5 = W5[off];
-            // five 24-bit biased values in 15 bytes; relu(hq) = max(u, bias) - bias, the bias cancels in the difference
+            // five 24-bit biased values in 15 bytes (the pad byte is zero); relu(hq) = max(u, bias) - bias, the bias
+            // cancels in the difference.  A padding entry may hold an mbarrier: any bits, its weights are zero
             const int v0 = h.x & 0xffffff;
             const int v1 = (int)(__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu);
             const int v2 = (int)(__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu);
             const int v3 = (int)((unsigned)h.z >> 8);
-            const int v4 = h.w & 0xffffff;
+            const int v4 = h.w;
             Dx += max(v0 + w.x, B0) - max(v0, B0);
             Dy += max(v1 + w.y, B1) - max(v1, B1);
             Dz += max(v2 + w.z, B2) - max(v2, B2);
@@ -246,18 +261,16 @@ __global__ void __launch_bounds__(NW * 32, 2)
           l2 = __reduce_add_sync(SO_FULL, l2);
           acc = ((long long)l2 << 42) + ((long long)l1 << 21) + (long long)l0;
         }
-        // Metropolis (OML/optimize_SA.py:108-116).  fp32 fast path: delta = sigma*c*acc, sign from the exact integer;
-        // it decides unless p = exp(delta/T) is within 1e-3 (relative) of u -- then the fp64 rule (decide_cold).
+        // Metropolis (OML/optimize_SA.py:108-116) as "delta > thr" (draw_batch_cold): the fp32 comparison decides unless
+        // the two sides are within 1e-5 (relative) of each other -- then the fp64 rule (decide_cold) with the redrawn u
         bool accept;
         {
-          const float Tf = tsc_f * t_b;
-          const bool up = sigma_pos ? (acc > 0) : (acc < 0);
-          const float pf = __expf(__fdividef((float)acc * k_f, Tf));
-          if (fast_ok && up && Tf > 0.f) {
-            accept = true;                          // delta > 0
-          } else if (fast_ok && !up && Tf > 1e-30f && u > 0.f && fabsf(pf - u) > 1e-3f * fmaxf(pf, u)) {
-            accept = pf > u;
+          const float x = (float)acc * k_f;
+          const float diff = x - thr;
+          if (fabsf(diff) > 1e-5f * fmaxf(fabsf(x), fabsf(thr))) {
+            accept = diff > 0.f;
           } else {
+            const float u = redraw_u_cold(P.uniforms, P.n_steps, P.step0, P.chain_id0 + c, c, P.seed, s);
             int r = decide_cold(acc, P.sv.y_scale, P.sv.c, tsc, P.temps, s, u, P.exact_guard, P.guard_tol);
             if (r & 2) {
               r = exact_decision_cold(P.sv, s_bits, d, f, lane, __dmul_rn(tsc, __ldg(P.temps + s)), u);
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
                   const unsigned v1 = (__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu) + (unsigned)w.y;
                   const unsigned v2 = (__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu) + (unsigned)w.z;
                   const unsigned v3 = ((unsigned)h.z >> 8) + (unsigned)w.w;
-                  const unsigned v4 = (unsigned)((h.w & 0xffffff) + w5);
+                  const unsigned v4 = (unsigned)(h.w + w5);
                   h.x = (int)(v0 | (v1 << 24));
                   h.y = (int)((v1 >> 8) | (v2 << 16));
                   h.z = (int)((v2 >> 16) | (v3 << 8));
@@ -297,8 +310,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
             bulk_wait_all();                          // at most one flip's stores in flight (every lane waits for its own groups)
             __syncwarp();
             {
-              const uint32_t src = stage0 + slot * stage_pitch;
-              const bool interior = use_tma && f1 - gb1 >= 0 && f1 - gb1 + gL <= d && f2 - gb2 >= 0 && f2 - gb2 + gseg <= d;
+              const uint32_t src = stage0 + c_off;
+              const bool interior = ((unsigned)(f1 - gb1) < lim1) & ((unsigned)(f2 - gb2) < lim2);
               if (interior) {
                 if (lane == 0) tma_store_3d(&tmap, (f1 - gb1) * (SI4 * 4), f2 - gb2, (int)c, src);
               } else {
@@ -347,12 +360,18 @@ __global__ void __launch_bounds__(NW * 32, 2)
         if (P.accept_out && lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
         __syncwarp();
       }
-      f_b = f_a; u_b = u_a; t_b = t_a;
-      f_a = f_q; u_a = u_q; t_a = t_q;
-      slot = slot + 1 == STAGES ? 0 : slot + 1;
+      f_b = f_a; thr_b = thr_a;
+      f_a = f_q; thr_a = thr_q;
+      p_off = c_off;
     }
     if (COMMIT == 0) bulk_wait_all();
     __syncwarp();
+    // the first two iterations of the next chain compute nothing: step the ring state back by two windows
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i) {
+      if (p_off == 0) { par ^= 1u; p_off = ring_bytes; }
+      p_off -= stage_pitch;
+    }
     for (int w = lane; w < P.W; w += 32) bits_g[w] = s_bits[w];
     if (lane == 0) {
       P.hi[c] = hi;
@@ -370,7 +389,7 @@ static size_t window_smem_bytes(int Q, int W, int stages, int nw = WARPS) {
   size_t st_i4 = window_stage_i4(Q);
   size_t i4 = 8 + 2 * st_i4 + (size_t)nw * stages * st_i4;
   size_t words = ((size_t)nw * W + 3) & ~(size_t)3;
-  return i4 * 16 + words * 4 + (size_t)nw * stages * 8 + 16 + 2 * st_i4 * 4;   // (+ the fifth-weight tables of PACKED)
+  return i4 * 16 + words * 4 + 16 + 2 * st_i4 * 4;   // (+ the fifth-weight tables of PACKED)
 }
 
 // int32 state [sites][20] -> 24-bit biased, five values per int4, four int4 (64 bytes) per site
@@ -471,6 +490,7 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
   long long want = (P.n_chains + WARPS - 1) / WARPS;
   int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
   if (blocks < 1) blocks = 1;
+  SO_REQUIRE(P.n_steps < 0x7ffffff0LL, "more than 2^31 steps in one launch: split the schedule");
   if (s->compact) {                              // 24-bit packed state: 4 int4 per site, all 32 lanes own slots
     const int Q = s->K * 4;
     g.stage_i4 = window_stage_i4(Q);

@@ -68,38 +68,56 @@ __device__ __forceinline__ bool near_cyclic(int a, int b, int r, int d) {   // c
 }
 
 // ---- cold paths, kept out of line so that they do not cost the hot loop registers ---------------------------------
-// lane-parallel draws of steps 32b .. 32b+31: packed site (f1 | f2 << 16), uniform, temperature.  Everything is
-// passed and returned BY VALUE: an address-taken argument would pin the caller's variables in local memory.
+// lane-parallel draws of steps 32b .. 32b+31: packed site (f1 | f2 << 16) and the fp32 DECISION THRESHOLD of the step.
+// The Metropolis rule (OML/optimize_SA.py:108-116) "accept iff delta > 0, or T > 0 and exp(delta / T) > u" is
+// "accept iff delta > thr" with thr = min(T ln u, 0) for T > 0 and u > 0, thr = 0 for T <= 0 (x = 0 is then a reject and is
+// left to the fp64 rule).  thr is computed here in fp64, once per step and lane, and rounded to fp32; the hot loop compares
+// the fp32 image of delta with it and falls back to the fp64 rule (decide_cold) whenever the two are closer than 1e-5
+// relative -- 50x the worst fp32 error of either side -- so every decision is the fp64 rule's.  thr = NaN (u = 0, exact_guard,
+// an fp32-denormal scale) sends the step to the fp64 rule unconditionally.
+// Everything is passed and returned BY VALUE: an address-taken argument would pin the caller's variables in local memory.
 struct Draw {
   int f;
-  float u;
-  double t;
+  float thr;
 };
+__device__ __forceinline__ float draw_u(const float *uniforms, long long n_steps, long long step0, long long chain_id,
+                                        long long c, unsigned long long seed, long long s, int N, int *f_out) {
+  if (uniforms) return __ldg(uniforms + c * n_steps + s);
+  unsigned long long step = (unsigned long long)(step0 + s), cid = (unsigned long long)chain_id;
+  uint32_t o[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), o);
+  if (f_out) *f_out = (int)__umulhi(o[0], (uint32_t)N);
+  return (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+}
 __device__ __noinline__ Draw draw_batch_cold(const double *temps, const int32_t *proposals, const float *uniforms,
                                              long long n_steps, long long step0, long long chain_id, long long c,
-                                             unsigned long long seed, int N, int d, long long b, int lane) {
+                                             unsigned long long seed, int N, int d, long long b, int lane, double tsc,
+                                             int fast_ok) {
   long long s = b * 32 + lane;
   Draw r;
   int f = 0;
-  r.u = 0.f;
-  r.t = 0.0;
+  r.thr = __int_as_float(0x7fc00000);
   if (s < n_steps) {
-    r.t = __ldg(temps + s);
-    if (proposals) {
-      f = __ldg(proposals + c * n_steps + s);
-      r.u = __ldg(uniforms + c * n_steps + s);
-    } else {
-      unsigned long long step = (unsigned long long)(step0 + s), cid = (unsigned long long)chain_id;
-      uint32_t o[4];
-      philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)cid, (uint32_t)(cid >> 32), (uint32_t)seed,
-                    (uint32_t)(seed >> 32), o);
-      f = (int)__umulhi(o[0], (uint32_t)N);
-      r.u = (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+    const float u = draw_u(uniforms, n_steps, step0, chain_id, c, seed, s, N, &f);
+    if (proposals) f = __ldg(proposals + c * n_steps + s);
+    const double T = __dmul_rn(tsc, __ldg(temps + s));
+    if (fast_ok) {
+      if (T > 0.0) {
+        if (u > 0.f) r.thr = (float)fmin(T * log((double)u), 0.0);
+      } else {
+        r.thr = 0.f;
+      }
     }
   }
   int f2 = f / d;
   r.f = (f - f2 * d) | (f2 << 16);
   return r;
+}
+// the uniform of ONE step again, for the fp64 rule (the hot loop carries only the threshold)
+__device__ __noinline__ float redraw_u_cold(const float *uniforms, long long n_steps, long long step0, long long chain_id,
+                                            long long c, unsigned long long seed, long long s) {
+  return draw_u(uniforms, n_steps, step0, chain_id, c, seed, s, 1, nullptr);
 }
 
 // the fp64 Metropolis rule (OML/optimize_SA.py:108-116) + the near-tie guard; bit 0 = accept, bit 1 = guard

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libso_b200.so")
+# SO_B200_LIB: another build of the same library (same-box A/B measurements of kernel changes)
+LIB_PATH = os.environ.get("SO_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libso_b200.so")
 
 SO_OK, SO_EINVAL, SO_ECUDA, SO_ENOMEM, SO_ESTATE = 0, -1, -2, -3, -4
 KIND_LSC, KIND_NH3 = 0, 1
