@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
   extern __shared__ __align__(128) unsigned char s_raw[];
   const int Q = P.sv.K * SI4;                     // int4 per window
   const int stage_i4 = g.stage_i4;                // window + zero-weight padding, multiple of 8 int4
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = __reduce_max_sync(SO_FULL, threadIdx.x >> 5);   // (uniform to the compiler: addresses derived from it stay in uniform registers)
   const int d = P.d;
   // shared layout: [per warp: STAGES stages][+W: stage_i4][-W: stage_i4][w2: 8 int4][per warp: bits][PACKED: fifth weights]
   // The mbarrier of a stage lives INSIDE the stage, in the first zero-weight padding entry behind the window (int4 index Q):
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int gb1 = g.b1, gb2 = g.b2, gL = g.L, gseg = g.n_seg;
   // a window is interior (one tensor-TMA box) iff 0 <= f1 - b1 <= d - L and 0 <= f2 - b2 <= d - n_seg: two unsigned tests
   const unsigned lim1 = g.use_tma ? (unsigned)(d - gL + 1) : 0u, lim2 = g.use_tma ? (unsigned)(d - gseg + 1) : 0u;
+  const bool record = P.accept_out != nullptr;
   const int n_steps = (int)P.n_steps;               // (the launcher refuses launches of 2^31 steps or more)
 
   // ring of stages, continuous over all chains of the warp: the k-th window the warp ever computes on sits in stage k % 3
@@ -127,9 +129,9 @@ __global__ void __launch_bounds__(NW * 32, 2)
   uint32_t p_off = 0, par = 1;
 
   for (;;) {
-    long long c = 0;
-    if (lane == 0) c = (long long)atomicAdd(P.counters, 1ULL);
-    c = __shfl_sync(SO_FULL, c, 0);
+    unsigned c32 = 0;
+    if (lane == 0) c32 = (unsigned)min(atomicAdd(P.counters, 1ULL), 0xffffffffULL);
+    const long long c = (long long)__reduce_max_sync(SO_FULL, c32);     // (uniform; the launcher refuses 2^32 chains or more)
     if (c >= P.n_chains) break;
     uint32_t *bits_g = P.bits + c * P.W;
     for (int w = lane; w < P.W; w += 32) s_bits[w] = bits_g[w];
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
             __syncwarp();
           }
         }
-        f_q = __shfl_sync(SO_FULL, batch.f, sp & 31);
+        f_q = __reduce_or_sync(SO_FULL, lane == (sp & 31) ? batch.f : 0);   // REDUX: the compiler knows the result is warp-uniform
         thr_q = __shfl_sync(SO_FULL, batch.thr, sp & 31);
         const int q1 = pk1(f_q), q2 = pk2(f_q);
         if (COMMIT == 0 && pend_f >= 0 && near_cyclic(q1, pk1(pend_f), gL - 1, d) && near_cyclic(q2, pk2(pend_f), gseg - 1, d)) {
@@ -357,7 +359,9 @@ __global__ void __launch_bounds__(NW * 32, 2)
         }
         hist1 = hist0;
         hist0 = accept ? fp : -1;
-        if (P.accept_out && lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
+        if (record) {
+          if (lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
+        }
         __syncwarp();
       }
       f_b = f_a; thr_b = thr_a;
@@ -491,6 +495,7 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
   int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
   if (blocks < 1) blocks = 1;
   SO_REQUIRE(P.n_steps < 0x7ffffff0LL, "more than 2^31 steps in one launch: split the schedule");
+  SO_REQUIRE(P.n_chains < 0xffffffffLL, "more than 2^32 chains in one handle");
   if (s->compact) {                              // 24-bit packed state: 4 int4 per site, all 32 lanes own slots
     const int Q = s->K * 4;
     g.stage_i4 = window_stage_i4(Q);
