@@ -103,11 +103,18 @@ int so_surrogate_destroy(so_surrogate *s);
  * 16 bytes) instead of 80.  Records then coincide with the 64-byte fill granule of the L2: a flip moves 3,136 bytes of
  * DRAM traffic instead of ~4,480.  Scores stay within the 1e-5 bar (tests); decisions are those of the same exact
  * integer arithmetic on the coarser grid, re-taken from the fp64 weights near ties when exact_guard is set.  Needs 17..20
- * hidden units, a rectangular-window descriptor (e.g. get_local_inds) and no tree gate; so_anneal then always runs the
+ * hidden units and a rectangular-window descriptor (e.g. get_local_inds); so_anneal then always runs the
  * pipelined window kernel.                                                                                       */
 int so_surrogate_create_compact(so_lattice *lat, int K, int H, const int32_t *offsets, const double *W1,
                                 const double *b1, const double *W2, double b2, double y_mean, double y_scale,
                                 so_surrogate **out);
+/* the compact state WITH the classifier gate of OML/train_surrogate.py:34-54 (same tree arrays as so_surrogate_create):
+ * so_anneal then runs the gated window kernel, whose per-row gate records (16 bytes per row, allocated by
+ * so_chains_attach) travel through the same TMA pipeline as the state.                                          */
+int so_surrogate_create_compact_gated(so_lattice *lat, int K, int H, const int32_t *offsets, const double *W1,
+                                      const double *b1, const double *W2, double b2, double y_mean, double y_scale,
+                                      int n_tree_nodes, const int32_t *feature, const double *thr, const int32_t *left,
+                                      const int32_t *right, const uint8_t *leaf_active, so_surrogate **out);
 /* quantisation exponents chosen at load: h grid 2^e_h, w2 grid 2^e_w, padded hidden width Hp              */
 int so_surrogate_info(const so_surrogate *s, int *K, int *H, int *Hp, int *e_h, int *e_w, int *gated);
 
@@ -151,7 +158,8 @@ typedef struct so_anneal_args {
   double guard_tol;          /* |delta - T ln u| below which the guard fires       */
   int variant;               /* 0 = auto; tests: 1 = row-per-lane global-memory kernel, 2 = generic flat kernel,
                                 3 = auto without the shared-memory-resident kernels of small lattices,
-                                4 = resident warp-per-chain kernel, 5 = resident CTA-per-chain kernel */
+                                4 = resident warp-per-chain kernel, 5 = resident CTA-per-chain kernel,
+                                6 = cached-gate kernel with global state (instead of the gated window kernel) */
 } so_anneal_args;
 
 typedef struct so_anneal_stats {

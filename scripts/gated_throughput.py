@@ -29,14 +29,20 @@ off = engine.local_offsets(3)
 W1, b1, w2, b2 = glorot_mlp(off, 20, 0)
 sweep = d * d
 temps = exp_schedule(0.05, 5 * sweep)
-for gated, variant in ((False, 0), (True, 0), (True, 1)):
+# gate off (window kernel) / gated window kernel on the int32 and on the packed state / cached-gate kernel (variant 6) /
+# row-per-lane kernel (variant 1)
+cases = ((False, 0, False), (True, 0, False), (True, 0, True), (True, 6, False), (True, 1, False))
+if len(sys.argv) > 3:
+    cases = [cases[int(i)] for i in sys.argv[3].split(",")]
+for gated, variant, compact in cases:
     tree = random_tree(49, depth, np.random.default_rng(0)) if gated else None
-    tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=tree)
+    tab = engine.SurrogateTables(lat, off, W1, b1, w2, b2, tree=tree, compact=compact)
     ch = engine.Chains(lat, n)
     ch.randomize(1, 0.5)
     ch.attach(tab)
     for i in range(3):          # sweeps 0, 1, 2 of a 5-sweep exponential schedule: acceptance falls as in a real run
         st = ch.anneal(temps[i * sweep:(i + 1) * sweep], seed=2, step0=i * sweep, variant=variant)
-        print("depth %d gated=%s variant=%d sweep %d: %.3e flip-evals/s (kernel %.1f ms, accept %.3f)" % (
-            depth, gated, variant, i, st["flips"] / st["kernel_ms"] * 1e3, st["kernel_ms"], st["accepted"] / st["flips"]), flush=True)
+        print("depth %d gated=%s variant=%d compact=%d %s sweep %d: %.3e flip-evals/s (kernel %.1f ms, accept %.3f)" % (
+            depth, gated, variant, compact, st["kernel"], i, st["flips"] / st["kernel_ms"] * 1e3, st["kernel_ms"],
+            st["accepted"] / st["flips"]), flush=True)
     ch.close()

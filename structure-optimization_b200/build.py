@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/so_api.cu", "csrc/so_desc.cu", "csrc/so_sa.cu", "csrc/so_sa_window.cu", "csrc/so_sa_resident.cu", "csrc/so_lsc.cu", "csrc/so_score_tc.cu", "csrc/so_train.cu", "csrc/so_tree.cu"]
+SOURCES = ["csrc/so_api.cu", "csrc/so_desc.cu", "csrc/so_sa.cu", "csrc/so_sa_window.cu", "csrc/so_sa_window_gated.cu", "csrc/so_sa_resident.cu", "csrc/so_lsc.cu", "csrc/so_score_tc.cu", "csrc/so_train.cu", "csrc/so_tree.cu"]
 HEADERS = ["csrc/so_internal.cuh", "csrc/so_window_common.cuh", "csrc/so_types.cuh", "../include/so_b200.h"]
 LIB = os.path.join(HERE, "libso_b200.so")
 

@@ -215,6 +215,7 @@ int so_chains_destroy(so_chains *c) {
   cudaFree(c->tscale_dev); cudaFree(c->counters_dev); cudaFree(c->xch_scratch); cudaFree(c->gate_scratch); cudaFree(c->temps_dev);
   cudaFree(c->type_hist_dev);
   cudaFree(c->tmp_hq_dev);
+  cudaFree(c->gate_meta_dev);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -248,6 +249,7 @@ static int refresh_types(so_chains *c, int64_t chain0, int64_t n) {
 }
 
 static int rescore(so_chains *c, int64_t chain0, int64_t n) {
+  c->meta_valid = 0;                               // the bits changed: the gated window kernel rebuilds its row records
   SO_TRY(refresh_types(c, chain0, n));
   if (!c->sur || n == 0) return SO_OK;
   NvtxRange nvtx_range("state build (first-layer state + objective sums from the bits)");
@@ -503,6 +505,7 @@ static int surrogate_create_impl(so_lattice *L, int K, int H, const int32_t *off
   s->offs_dev = nullptr; s->W1q_dev = s->b1q_dev = s->w2q_dev = nullptr; s->W1d_dev = s->b1d_dev = s->w2d_dev = nullptr;
   s->t_feature_dev = s->t_left_dev = s->t_right_dev = nullptr; s->t_thr_dev = nullptr; s->t_active_dev = nullptr;
   s->t_packed_dev = nullptr;
+  s->wtree_dev = nullptr;
   // fixed-point grids (identical to oracle/surrogate.py quantize)
   double bound = 0.0, wmax = 0.0;
   for (int j = 0; j < H; ++j) {
@@ -580,10 +583,10 @@ static int surrogate_create_impl(so_lattice *L, int K, int H, const int32_t *off
   }
   if (rc == SO_OK) rc = upload(&s->Wst_dev, Wst.data(), (size_t)K * Hp);
   if (s->compact) {
-    // the packed state serves the pipelined window kernel only: 17..20 hidden units, rectangular window, no gate
-    if (!(Hp == 20 && s->win_ok && !s->gated)) {
+    // the packed state serves the pipelined window kernels only: 17..20 hidden units, rectangular window
+    if (!(Hp == 20 && s->win_ok)) {
       so_surrogate_destroy(s);
-      so_set_error("the compact (24-bit) state needs 17..20 hidden units, a rectangular-window descriptor and no tree gate");
+      so_set_error("the compact (24-bit) state needs 17..20 hidden units and a rectangular-window descriptor");
       return SO_EINVAL;
     }
     std::vector<int32_t> bias(Hp, 0);
@@ -624,6 +627,28 @@ static int surrogate_create_impl(so_lattice *L, int K, int H, const int32_t *off
       packed[i] = nd;
     }
     if (rc == SO_OK) rc = upload(&s->t_packed_dev, packed.data(), (size_t)n_tree_nodes);
+    // 8-byte nodes of the gated window kernel (so_sa_window_gated.cu): children by the value of the tested bit, the tested
+    // column as patch-relative coordinates and as the window position its rows sit at
+    const int Lw = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
+    if (rc == SO_OK && s->win_ok && n_tree_nodes <= 65535 && Lw <= 16 && nseg <= 16 && K <= 63) {
+      std::vector<uint2> wt((size_t)n_tree_nodes);
+      for (int i = 0; i < n_tree_nodes; ++i) {
+        uint2 nd;
+        if (feature[i] < 0) {
+          nd.x = 0;
+          nd.y = (1u | (leaf_active[i] ? 2u : 0u)) << 24;
+        } else {
+          const int o1 = offsets[2 * feature[i]], o2 = offsets[2 * feature[i] + 1];
+          const unsigned c0 = (0.0 <= thr[i]) ? (unsigned)left[i] : (unsigned)right[i];     // bit 0: x = 0 <= thr ?
+          const unsigned c1 = (1.0 <= thr[i]) ? (unsigned)left[i] : (unsigned)right[i];     // bit 1: x = 1 <= thr ?
+          const unsigned pc = (unsigned)((s->win_b2 - o2) * Lw + (s->win_b1 - o1));
+          nd.x = c0 | (c1 << 16);
+          nd.y = (unsigned)(o1 - s->win_a1) | ((unsigned)(o2 - s->win_a2) << 8) | (pc << 16) | ((c0 != c1 ? 4u : 0u) << 24);
+        }
+        wt[i] = nd;
+      }
+      rc = upload((uint2 **)&s->wtree_dev, wt.data(), wt.size());
+    }
   }
   if (rc != SO_OK) { so_surrogate_destroy(s); return rc; }
   *out = s;
@@ -644,6 +669,14 @@ int so_surrogate_create_compact(so_lattice *L, int K, int H, const int32_t *offs
                                nullptr, 22, out);
 }
 
+int so_surrogate_create_compact_gated(so_lattice *L, int K, int H, const int32_t *offsets, const double *W1, const double *b1,
+                                      const double *W2, double b2, double y_mean, double y_scale, int n_tree_nodes,
+                                      const int32_t *feature, const double *thr, const int32_t *left, const int32_t *right,
+                                      const uint8_t *leaf_active, so_surrogate **out) {
+  return surrogate_create_impl(L, K, H, offsets, W1, b1, W2, b2, y_mean, y_scale, n_tree_nodes, feature, thr, left, right,
+                               leaf_active, 22, out);
+}
+
 int so_surrogate_destroy(so_surrogate *s) {
   if (!s) return SO_OK;
   cudaSetDevice(s->device);
@@ -651,7 +684,7 @@ int so_surrogate_destroy(so_surrogate *s) {
   cudaFree(s->tc_image_dev); cudaFree(s->Wst_dev); cudaFree(s->offs_dev); cudaFree(s->W1q_dev); cudaFree(s->b1q_dev); cudaFree(s->w2q_dev);
   cudaFree(s->W1d_dev); cudaFree(s->b1d_dev); cudaFree(s->w2d_dev);
   cudaFree(s->t_feature_dev); cudaFree(s->t_thr_dev); cudaFree(s->t_left_dev); cudaFree(s->t_right_dev);
-  cudaFree(s->t_active_dev); cudaFree(s->t_packed_dev);
+  cudaFree(s->t_active_dev); cudaFree(s->t_packed_dev); cudaFree(s->wtree_dev);
   delete s;
   return SO_OK;
 }
@@ -665,6 +698,31 @@ int so_surrogate_info(const so_surrogate *s, int *K, int *H, int *Hp, int *e_h, 
   if (e_w) *e_w = s->e_w;
   if (gated) *gated = s->gated;
   return SO_OK;
+}
+
+// CUtensorMap over `base` viewed as int32 [n_chains][d][d * site_words], box = one window (Lw sites x nseg rows); 1 = ok
+static int window_tensor_map(CUtensorMap *map, void *base, const so_lattice *L, int64_t n_chains, int site_words, int Lw,
+                             int nseg) {
+  if ((uint64_t)Lw * site_words > 256 || nseg > 256) return 0;
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  int ok = 0;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+      qres == cudaDriverEntryPointSuccess) {
+    cuuint64_t gdim[3] = {(cuuint64_t)L->d * site_words, (cuuint64_t)L->d, (cuuint64_t)n_chains};
+    cuuint64_t gstr[2] = {(cuuint64_t)L->d * site_words * 4, (cuuint64_t)L->N * site_words * 4};
+    cuuint32_t box[3] = {(cuuint32_t)(Lw * site_words), (cuuint32_t)nseg, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = ((EncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, base, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ok = (cr == CUDA_SUCCESS) ? 1 : 0;
+  }
+  (void)cudaGetLastError();
+  return ok;
 }
 
 int so_chains_attach(so_chains *c, so_surrogate *s) {
@@ -688,29 +746,29 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
     return SO_ENOMEM;
   }
   c->sur = s;
-  // tensor map over hq viewed as int32 [n_chains][d][d*Hp]; one box = the window of a flip (so_sa_window.cu)
+  // tensor map over hq viewed as int32 [n_chains][d][d*site_words]; one box = the window of a flip (so_sa_window.cu).  Gated
+  // window descriptors also get the per-row records of so_sa_window_gated.cu (16 bytes per row) and their map.
   c->tmap_ok = 0;
-  if (s->win_ok && !s->gated) {
+  c->tmap_meta_ok = 0;
+  c->meta_valid = 0;
+  cudaFree(c->gate_meta_dev);
+  c->gate_meta_dev = nullptr;
+  if (s->win_ok) {
     const int Lw = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
-    if ((uint64_t)Lw * site_words <= 256 && nseg <= 256) {
-      typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-      void *fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
-          qres == cudaDriverEntryPointSuccess) {
-        cuuint64_t gdim[3] = {(cuuint64_t)L->d * site_words, (cuuint64_t)L->d, (cuuint64_t)c->n_chains};
-        cuuint64_t gstr[2] = {(cuuint64_t)L->d * site_words * 4, (cuuint64_t)L->N * site_words * 4};
-        cuuint32_t box[3] = {(cuuint32_t)(Lw * site_words), (cuuint32_t)nseg, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult cr = ((EncodeFn)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, c->hq_dev, gdim, gstr, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        c->tmap_ok = (cr == CUDA_SUCCESS) ? 1 : 0;
+    c->tmap_ok = window_tensor_map(&c->tmap, c->hq_dev, L, c->n_chains, site_words, Lw, nseg);
+    if (s->gated && s->wtree_dev && c->tmap_ok) {
+      if (cudaMalloc(&c->gate_meta_dev, (size_t)c->n_chains * L->N * 16) == cudaSuccess) {
+        c->tmap_meta_ok = window_tensor_map(&c->tmap_meta, c->gate_meta_dev, L, c->n_chains, 4, Lw, nseg);
+      } else {
+        c->gate_meta_dev = nullptr;
+        (void)cudaGetLastError();                  // no records: the cached-gate kernel with its own scratch serves the gate
       }
-      (void)cudaGetLastError();
     }
+  }
+  if (s->compact && s->gated && !so_window_gated_ok(c)) {
+    c->sur = nullptr;
+    so_set_error("the compact (24-bit) gated state is served by the gated window kernel only, which cannot run this shape");
+    return SO_EINVAL;
   }
   SO_TRY(rescore(c, 0, c->n_chains));
   SO_CUDA(cudaStreamSynchronize(c->stream));
@@ -910,6 +968,7 @@ const char *so_kernel_name(int kernel_id) {
     case SO_K_RESIDENT: return "sa_resident_kernel";
     case SO_K_GATE_INDEX: return "sa_resident_kernel<RES=false> (cached gates, state in HBM)";
     case SO_K_WINDOW: return "sa_window_kernel";
+    case SO_K_WINDOW_GATED: return "sa_window_gated_kernel";
     case SO_K_FLAT: return "sa_flat_kernel";
     case SO_K_GATED: return "sa_gated_kernel";
     case SO_K_ANALYTICAL: return "lsc_anneal_kernel";

@@ -78,6 +78,7 @@ struct so_surrogate {
   int compact;                                  // 24-bit packed state, 64 bytes per site (so_surrogate_create_compact)
   int32_t *bias24_dev;                          // compact: [Hp] stored value = hq + bias
   int32_t *Wst24_dev;                           // compact: [K*4 slots][8] = five weights of the slot's hidden units + pad
+  void *wtree_dev;                              // gated window kernel: 8-byte tree nodes (so_sa_window_gated.cu) or NULL
   unsigned char *tc_image_dev;                  // B operand of the tensor-core scorer (so_score_tc.cu) or NULL
   int tc_ok;
 };
@@ -106,6 +107,11 @@ struct so_chains {
   int32_t *type_hist_dev;               // tracked histograms: [n_chains][8] NH3 exported + [n_chains][3] LSC, or null
   CUtensorMap tmap;                     // hq as int32 [n_chains][d][d*Hp], box = one window (so_sa_window.cu)
   int tmap_ok;
+  void *gate_meta_dev;                  // gated window kernel: one 16-byte record per row {T lo, T hi | gate << 31, 0, 0}
+  CUtensorMap tmap_meta;                // the records as int32 [n_chains][d][d*4], box = one window
+  int tmap_meta_ok;
+  mutable int meta_valid;               // the records describe the current bits (set by the gated window kernel, cleared by
+                                        // everything else that changes bits)
 };
 
 // ---- device-side views ------------------------------------------------------------------------------
@@ -184,13 +190,15 @@ int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_
                         double *rate_dev, cudaStream_t st);
 // kernel ids reported in so_anneal_stats.kernel_id (names: so_kernel_name)
 enum { SO_K_NONE = 0, SO_K_TEAM = 1, SO_K_RESIDENT = 2, SO_K_GATE_INDEX = 3, SO_K_WINDOW = 4, SO_K_FLAT = 5, SO_K_GATED = 6,
-       SO_K_ANALYTICAL = 7 };   // (the window kernel on the 24-bit packed state reports SO_K_WINDOW)
+       SO_K_ANALYTICAL = 7, SO_K_WINDOW_GATED = 8 };   // (the window kernel on the 24-bit packed state reports SO_K_WINDOW)
 int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int *kernel_id);
 int so_launch_islands(uint32_t *bits_dev, int64_t n, int d, int N, int W, const int32_t *index_dev, int n_strucs, int n_mutate,
                       int32_t *scratch_dev, cudaStream_t st);
 int so_launch_pack24(const int32_t *src_dev, void *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st);
 int so_launch_unpack24(const void *src_dev, int32_t *dst_dev, int64_t n_sites, const int32_t *bias_dev, cudaStream_t st);
 int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t st);
+bool so_window_gated_ok(const so_chains *c);
+int so_launch_anneal_window_gated(const so_chains *c, const SaParams &P, cudaStream_t st, int build_records);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);
 bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem, int min_warps_per_sm = 8);

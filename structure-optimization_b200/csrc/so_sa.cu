@@ -587,10 +587,18 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int
   int dev = c->lat->device, n_sm = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   SO_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long), st));   // work counter
+  // row records of the gated window kernel: current only if that kernel ran last and nothing else touched the bits since
+  const int records_current = c->meta_valid;
+  c->meta_valid = 0;
   if (s->compact) {          // 24-bit packed state: the pipelined window kernel is the only reader
     if (!(P.variant == 0 || P.variant == 3)) {
       so_set_error("the compact state is served by the window kernel only (variant 0 or 3, got %d)", P.variant);
       return SO_EINVAL;
+    }
+    if (s->gated) {
+      int rc = so_launch_anneal_window_gated(c, P, st, !records_current);
+      if (rc == SO_OK) { kid = SO_K_WINDOW_GATED; c->meta_valid = 1; }
+      return rc;
     }
     return kid = SO_K_WINDOW, so_launch_anneal_window(c, P, st);
   }
@@ -601,8 +609,14 @@ int so_launch_anneal(const so_chains *c, const SaParams &P, cudaStream_t st, int
   if ((P.variant == 0 && so_resident_plan(s, P.N, P.W, nullptr, nullptr)) ||
       (P.variant == 4 && so_resident_plan(s, P.N, P.W, nullptr, nullptr, 1)))
     return kid = SO_K_RESIDENT, so_launch_anneal_resident(c, P, st);
-  // gated, large lattice: cached gates + path index, only the active rows are read (so_sa_resident.cu)
-  if ((P.variant == 0 || P.variant == 3) && so_gate_index_ok(s, P.N, P.W))
+  // gated window descriptor on a large lattice: gate records ride the TMA pipeline of the window kernel (so_sa_window_gated.cu)
+  if ((P.variant == 0 || P.variant == 3) && so_window_gated_ok(c)) {
+    int rc = so_launch_anneal_window_gated(c, P, st, !records_current);
+    if (rc == SO_OK) { kid = SO_K_WINDOW_GATED; c->meta_valid = 1; }
+    return rc;
+  }
+  // gated, any descriptor: cached gates + path index, only the active rows are read (so_sa_resident.cu); variant 6 asks for it
+  if ((P.variant == 0 || P.variant == 3 || P.variant == 6) && so_gate_index_ok(s, P.N, P.W))
     return kid = SO_K_GATE_INDEX, so_launch_anneal_gate_index(c, P, st);
   if (!s->gated && (P.variant == 0 || P.variant == 3) && s->win_ok && s->K * s->HP4 <= 256 &&
       so_window_smem_bytes(s->K * s->HP4, P.W, 3) <= 113 * 1024) {

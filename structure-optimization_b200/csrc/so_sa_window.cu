@@ -491,6 +491,7 @@ int so_launch_anneal_window(const so_chains *c, const SaParams &P, cudaStream_t 
   WinGeom g;
   g.b1 = s->win_b1; g.b2 = s->win_b2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
   g.use_tma = c->tmap_ok;
+  g.tab_i4 = 0;
   long long want = (P.n_chains + WARPS - 1) / WARPS;
   int blocks = (int)(want < (long long)n_sm * 2 ? want : (long long)n_sm * 2);
   if (blocks < 1) blocks = 1;

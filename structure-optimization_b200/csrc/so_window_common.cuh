@@ -44,6 +44,7 @@ struct WinGeom {
   int use_tma;       // interior windows go through one tensor-TMA box
   int stage_i4;      // int4 per shared-memory stage: window + zero-weight padding, multiple of 8 (128 B)
   int nslots;        // lane slots per window: ceil(Q / STRIDE)
+  int tab_i4;        // gated kernel: entries of the weight tables (state slots + zero padding)
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2,

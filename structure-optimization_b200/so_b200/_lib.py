@@ -67,6 +67,9 @@ PROTOTYPES = {
     "so_surrogate_destroy": (C.c_int, [C.c_void_p]),
     "so_surrogate_create_compact": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, c_f64p, c_f64p, c_f64p, C.c_double,
                                               C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
+    "so_surrogate_create_compact_gated": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, c_f64p, c_f64p, c_f64p, C.c_double,
+                                                    C.c_double, C.c_double, C.c_int, c_i32p, c_f64p, c_i32p, c_i32p, c_u8p,
+                                                    C.POINTER(C.c_void_p)]),
     "so_surrogate_info": (C.c_int, [C.c_void_p, c_intp, c_intp, c_intp, c_intp, c_intp, c_intp]),
     "so_chains_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "so_score": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_f64p]),

@@ -61,7 +61,8 @@ class SurrogateTables(object):
 
     def __init__(self, lattice, offsets, W1, b1, w2, b2, y_mean=0.0, y_scale=1.0, tree=None, compact=False):
         """compact=True: 24-bit packed first-layer state, 64 bytes per site (so_surrogate_create_compact): window
-        descriptors, 17..20 hidden units, no gate; so_anneal then runs the pipelined window kernel on 20 % fewer bytes."""
+        descriptors, 17..20 hidden units; so_anneal then runs the pipelined window kernel on 20 % fewer bytes (with a tree:
+        so_surrogate_create_compact_gated and the gated window kernel)."""
         self.lib = B.load()
         self.lattice = lattice
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -83,9 +84,12 @@ class SurrogateTables(object):
             f = t = l = r = a = None
             n_nodes = 0
         self.compact = bool(compact)
-        if compact:
-            if tree is not None:
-                raise ValueError("the compact state does not support a tree gate")
+        if compact and tree is not None:
+            B.check(self.lib.so_surrogate_create_compact_gated(
+                lattice.h, K, H, _p(offsets, B.c_i32p), _p(W1, B.c_f64p), _p(b1, B.c_f64p), _p(w2, B.c_f64p),
+                float(np.asarray(b2).reshape(-1)[0]), float(y_mean), float(y_scale), n_nodes, _p(f, B.c_i32p),
+                _p(t, B.c_f64p), _p(l, B.c_i32p), _p(r, B.c_i32p), _p(a, B.c_u8p), C.byref(self.h)))
+        elif compact:
             B.check(self.lib.so_surrogate_create_compact(
                 lattice.h, K, H, _p(offsets, B.c_i32p), _p(W1, B.c_f64p), _p(b1, B.c_f64p), _p(w2, B.c_f64p),
                 float(np.asarray(b2).reshape(-1)[0]), float(y_mean), float(y_scale), C.byref(self.h)))

@@ -298,19 +298,88 @@ def _random_tree(K, depth, seed, grow=0.8):
                 right=np.array(right, np.int32), active=np.array(active, np.uint8))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 6])
 @pytest.mark.parametrize("d,T0", [(24, 0.05), (24, 2.0), (40, 0.3), (48, 1.0)])
 def test_sa_gated_local_large_lattice(eng, d, T0, variant):
     """Tree gate on lattices too large for the warp-per-chain resident kernel: 20 chains run on the CTA-per-chain
-    kernel (variant 0, state in up to 227 KB of shared memory), the cached-gate kernel with global state (variant 3:
-    gate bits + path index, only active rows read) and the row-per-lane kernel (variant 1), all against the oracle;
-    hot runs exercise the index upkeep on accept."""
+    kernel (variant 0, state in up to 227 KB of shared memory), the gated window kernel (variant 3: gate records in the
+    TMA pipeline), the cached-gate kernel with global state (variant 6: gate bits + path index, only active rows read)
+    and the row-per-lane kernel (variant 1), all against the oracle; hot runs exercise the record / index upkeep on accept."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=60 + d)
     p.tree = _random_tree(49, 7, seed=d)
     r = _run_sa(eng, d, p, n_chains=20, steps=1500, seed=70 + d, T0=T0, variant=variant,
                 cooling="const" if T0 > 1 else "exp")
     if T0 > 1:
         assert r["acc"].mean() > 0.1
+
+
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("d,n,steps,T0,depth", [(7, 24, 900, 2.0, 8), (9, 24, 900, 1.0, 6), (13, 40, 900, 2.0, 9), (20, 300, 500, 1.0, 8),
+                                                (33, 600, 300, 0.5, 8), (96, 48, 1500, 1.0, 8)])
+def test_sa_window_gated_kernel(eng, d, n, steps, T0, depth, compact):
+    """The gated window kernel (tree gate + 7x7 window, state and per-row gate records through the TMA pipeline) on the
+    int32 and on the 24-bit packed state: accept vectors, occupancies, exact sums, active-row counts and the whole
+    first-layer state equal the fixed-point oracle; hot chains on lattices from 7x7 (every window wraps, the bit patch
+    holds the flipped site several times, every prefetched window is stale) to 96x96; then the same steps in several
+    launches (records kept between launches), after outside changes of the bits (records rebuilt), and from Philox draws."""
+    from oracle import c_oracle
+    N = d * d
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=300 + d, y_mean=0.05, y_scale=1.3)
+    p.tree = _random_tree(49, depth, seed=400 + d)
+    q = S.quantize(p, bits="packed24") if compact else S.quantize(p)
+    lat = eng.Lattice(d, "NH3")
+    tab = eng.SurrogateTables(lat, p.offsets, p.W1, p.b1, p.w2, p.b2, p.y_mean, p.y_scale, tree=p.tree, compact=compact)
+    rng = np.random.default_rng(d)
+    x0 = (rng.random((n, N)) < 0.5).astype(np.uint8)
+    prop = rng.integers(0, N, (n, steps)).astype(np.int32)
+    u = rng.random((n, steps), dtype=np.float32)
+    temps = SA.schedule("const", T0, steps)
+    ch = eng.Chains(lat, n)
+    ch.set_occupancy(x0)
+    ch.attach(tab)
+    ch.track_types(True)
+    st, acc = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True, variant=3)
+    assert st["kernel"] == "sa_window_gated_kernel" and st["accepted"] > 0.05 * st["flips"]
+    o = c_oracle.anneal_fixed_many(p, q, d, x0, temps, prop, u)
+    assert (acc.astype(bool) == o["accept"]).all()
+    x1 = ch.get_occupancy()
+    assert (x1 == o["x"]).all()
+    of, hi, lo, na = ch.objective(sums=True)
+    assert (hi == o["hi"]).all() and (lo == o["lo"]).all() and (of == o["OF"]).all() and (na == o["n_act"]).all()
+    hq1, _ = S.preact_fixed(p, q, x1[n // 2], d)
+    assert (ch.preact(n // 2)[:, :20] == hq1[:, :20]).all()
+    assert (ch.score() == of).all()
+    lh, ne = ch.type_histograms()
+    assert (ne == ST.nh3_export_hist(ST.nh3_types(x1, d))).all()
+    # the same steps in four launches: the records stay valid between launches of this kernel ...
+    ch.set_occupancy(x0)
+    cuts = (0, steps // 3, steps // 3 + 1, steps // 2, steps)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s2 = ch.anneal(temps[a:b], step0=a, proposals=prop[:, a:b], uniforms=u[:, a:b], variant=3)
+        assert s2["kernel"] == "sa_window_gated_kernel"
+    assert (ch.get_occupancy() == x1).all() and (ch.objective() == of).all()
+    # ... and are rebuilt after the bits changed behind its back (another kernel, set_occupancy)
+    if not compact:
+        ch.set_occupancy(x0)
+        h = steps // 2
+        ch.anneal(temps[:h], proposals=prop[:, :h], uniforms=u[:, :h], variant=1)
+        ch.anneal(temps[h:], step0=h, proposals=prop[:, h:], uniforms=u[:, h:], variant=3)
+        assert (ch.get_occupancy() == x1).all() and (ch.objective() == of).all()
+    ch.set_occupancy(x0)
+    ch.anneal(temps, seed=3, variant=3)
+    xa, ofa = ch.get_occupancy(), ch.objective()
+    ch.set_occupancy(x0)
+    ch.anneal(temps, seed=3, variant=3)
+    assert (ch.get_occupancy() == xa).all() and (ch.objective() == ofa).all()
+    assert (ch.score() == ofa).all()
+    # near ties re-decided from the fp64 weights: decisions equal the fp64 rule
+    ch.set_occupancy(x0)
+    tol = 8.0 * np.sqrt(tab.K) * np.ldexp(1.0, tab.e_h) * abs(p.y_scale) * float(np.abs(p.w2).sum())
+    m = min(n, 16)
+    _, acc2 = ch.anneal(temps, proposals=prop, uniforms=u, want_accept=True, exact_guard=True, guard_tol=tol, variant=3)
+    o64 = c_oracle.anneal_fp64_many(p, d, x0[:m], temps, prop[:m], u[:m], margin_thr=1e-9)
+    ok = o64["n_below"] == 0
+    assert (acc2[:m].astype(bool)[ok] == o64["accept"][ok]).all() and ok.mean() > 0.9
 
 
 @pytest.mark.parametrize("variant", [4, 5])
