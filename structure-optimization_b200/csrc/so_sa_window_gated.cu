@@ -40,17 +40,29 @@ __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned s) {   // v <
   return r;
 }
 
-__device__ __forceinline__ int walk_patch(const uint2 *tree, const uint32_t *patch, int p1, int p2, unsigned &tlo,
-                                          unsigned &thi) {
+// gate of the row at window position (p1, p2) on the patch (the structure AFTER the flip); one 8-byte node and one patch word
+// per level, byte fields taken with PRMT
+template <class TreePtr>
+__device__ __forceinline__ unsigned walk_gate(TreePtr tree, const uint32_t *patch, int p1, int p2) {
   uint2 nd = tree[0];
-  tlo = 0; thi = 0;
+  while (!(nd.y & 0x01000000u)) {
+    const unsigned u1 = __byte_perm(nd.y, 0u, 0x4440), u2 = __byte_perm(nd.y, 0u, 0x4441);
+    const unsigned bit = (patch[p2 + u2] >> (p1 + u1)) & 1u;
+    nd = tree[(nd.x >> (bit << 4)) & 0xffffu];
+  }
+  return (nd.y >> 25) & 1u;
+}
+// the same walk, also collecting the window positions the path marks (accepted flips only): returns {T lo, T hi | g << 31}
+__device__ __noinline__ uint2 walk_mark_cold(const uint2 *tree, const uint32_t *patch, int p1, int p2) {
+  uint2 nd = tree[0];
+  unsigned tlo = 0, thi = 0;
   while (!(nd.y & 0x01000000u)) {
     const unsigned u1 = nd.y & 0xffu, u2 = (nd.y >> 8) & 0xffu, pc = (nd.y >> 16) & 0xffu;
     const unsigned bit = (patch[p2 + u2] >> (p1 + u1)) & 1u;
     if (nd.y & 0x04000000u) { tlo |= shl_clamp(1u, pc); thi |= shl_clamp(1u, pc - 32u); }
-    nd = tree[bit ? (nd.x >> 16) : (nd.x & 0xffffu)];
+    nd = tree[(nd.x >> (bit << 4)) & 0xffffu];
   }
-  return (int)((nd.y >> 25) & 1u);
+  return make_uint2(tlo, thi | (((nd.y >> 25) & 1u) << 31));
 }
 
 // the same walk on the chain's bit-plane (record build at launch start): returns {T lo, T hi | g << 31}
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int Wpad = P.W + 1;
   // shared layout: [per warp: STAGES stages of (state Q | pad to 128 B | records K | the stage's mbarrier | padding)]
   // [+W][-W][zero W: tab_i4 int4 each][w2: 8 int4][per warp: bits W + 1][fifth weights +, -, zero: tab_i4 ints each (PACKED)]
-  // [per warp: patch 32 words][tree]
+  // [per warp: patch 32 words | 64 + 64 bytes of lists][tree]
   unsigned char *s_stage = s_raw + (size_t)warp * STAGES * stage_i4 * 16;
   int4 *s_Wp = (int4 *)s_raw + (size_t)NW * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + tab_i4;
@@ -150,8 +162,9 @@ __global__ void __launch_bounds__(NW * 32, 2)
   int *s_W5p = (int *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * Wpad + 3) & ~(size_t)3));
   int *s_W5n = s_W5p + (PACKED ? tab_i4 : 0);
   int *s_W5z = s_W5n + (PACKED ? tab_i4 : 0);
-  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 32;
-  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 32);
+  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 64;       // patch rows, then two byte lists
+  unsigned char *s_list = (unsigned char *)(s_patch + 32), *s_res = s_list + 64;
+  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 64);
   const uint2 *tree = wg.tree_smem ? s_tree_buf : wg.tree;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   for (int q = threadIdx.x; q < tab_i4; q += blockDim.x) {
@@ -201,6 +214,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int pb2 = (lane + 32) / gL, pb1 = (lane + 32) - pb2 * gL;
   const bool va = lane < K, vb = lane + 32 < K;
   const int site0 = lane / SI4;                     // window site of the lane's slot 0 (slot it: site0 + SPP * it)
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   uint32_t p_off = 0, par = 1;
 
@@ -309,35 +323,40 @@ __global__ void __launch_bounds__(NW * 32, 2)
         if (vb) mb = *(const uint2 *)(stg0 + QA + lane + 32);
         const unsigned ta = (ma.x >> lane) & 1u, tb = (mb.y >> lane) & 1u & (unsigned)vb;
         unsigned g1a = ma.y >> 31, g1b = mb.y >> 31;
-        uint2 na = ma, nb = mb;                      // records after the flip
         const unsigned walk_a = __ballot_sync(SO_FULL, ta), walk_b = __ballot_sync(SO_FULL, tb);
-        if (walk_a | walk_b) {
+        const int n_walk = __popc(walk_a) + __popc(walk_b);
+        if (n_walk) {
+          // the rows to walk (about depth / K of the window) are compacted onto the first lanes: one round of walks
           if (lane < PH) s_patch[lane] = patch_row(s_bits, d, wrap(f2 - (gseg - 1) + lane, d), wrap(f1 - (gL - 1), d), PW, f1, f2);
+          if (ta) s_list[__popc(walk_a & lt_mask)] = (unsigned char)lane;
+          if (tb) s_list[__popc(walk_a) + __popc(walk_b & lt_mask)] = (unsigned char)(lane + 32);
           __syncwarp();
-          if (ta) {
-            g1a = (unsigned)walk_patch(tree, s_patch, pa1, pa2, na.x, na.y);
-            na.y |= g1a << 31;
-          }
-          if (tb) {
-            g1b = (unsigned)walk_patch(tree, s_patch, pb1, pb2, nb.x, nb.y);
-            nb.y |= g1b << 31;
+          for (int base = 0; base < n_walk; base += 32) {
+            if (base + lane < n_walk) {
+              const int p = s_list[base + lane];
+              const int p2 = p / gL, p1 = p - p2 * gL;
+              s_res[p] = (unsigned char)(wg.tree_smem ? walk_gate(s_tree_buf, s_patch, p1, p2) : walk_gate(wg.tree, s_patch, p1, p2));
+            }
           }
           __syncwarp();
+          if (ta) g1a = s_res[lane];
+          if (tb) g1b = s_res[lane + 32];
         }
         const unsigned A_lo = __ballot_sync(SO_FULL, ma.y >> 31), A_hi = __ballot_sync(SO_FULL, mb.y >> 31);
         const unsigned N_lo = __ballot_sync(SO_FULL, g1a), N_hi = __ballot_sync(SO_FULL, g1b);
         const unsigned both_lo = A_lo & N_lo, both_hi = A_hi & N_hi;
         const unsigned sw_lo = A_lo ^ N_lo, sw_hi = A_hi ^ N_hi;
         // ---- relu differences of the rows active on both sides: inactive rows read the zero weight table -------
+        // the three tables (+W, -W, zero) are contiguous: one index offset selects the table of a slot
         const int4 *Wl = (xbit ? s_Wn : s_Wp) + lane;
-        const int4 *Wz = s_Wz + lane;
+        const int4 *Wt = s_Wp + lane;
+        const int dir_off = xbit ? tab_i4 : 0, zero_off = 2 * tab_i4;
         // bit (SPP * it) of (both >> site0) <=> the site of slot `it` is active on both sides
         const unsigned m_lo = __funnelshift_r(both_lo, both_hi, site0), m_hi = both_hi >> site0;
         int Dx = 0, Dy = 0, Dz = 0, Dw = 0;
         long long acc;
         if constexpr (PACKED) {
-          const int *W5 = (xbit ? s_W5n : s_W5p) + lane;
-          const int *W5z = s_W5z + lane;
+          const int *W5t = s_W5p + lane;
           int Dv = 0;
 #pragma unroll
           for (int it = 0; it < nslots; ++it) {
@@ -345,8 +364,9 @@ __global__ void __launch_bounds__(NW * 32, 2)
             const int sb = SPP * it;
             const bool act = sb < 32 ? ((m_lo >> sb) & 1u) : ((m_hi >> (sb - 32)) & 1u);
             const int4 h = stg[off];
-            const int4 w = (act ? Wl : Wz)[off];
-            const int w5 = (act ? W5 : W5z)[off];
+            const int wi = (act ? dir_off : zero_off) + off;
+            const int4 w = Wt[wi];
+            const int w5 = W5t[wi];
             const int v0 = h.x & 0xffffff;
             const int v1 = (int)(__funnelshift_r((unsigned)h.x, (unsigned)h.y, 24) & 0xffffffu);
             const int v2 = (int)(__funnelshift_r((unsigned)h.y, (unsigned)h.z, 16) & 0xffffffu);
@@ -367,7 +387,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
             const int sb = SPP * it;
             const bool act = sb < 32 ? ((m_lo >> sb) & 1u) : ((m_hi >> (sb - 32)) & 1u);
             const int4 h = stg[off];
-            const int4 w = (act ? Wl : Wz)[off];
+            const int4 w = Wt[(act ? dir_off : zero_off) + off];
             Dx += max(h.x + w.x, 0) - max(h.x, 0);
             Dy += max(h.y + w.y, 0) - max(h.y, 0);
             Dz += max(h.z + w.z, 0) - max(h.z, 0);
@@ -389,25 +409,31 @@ __global__ void __launch_bounds__(NW * 32, 2)
         if (switching) {
           long long ph = 0;
           int pl = 0;
-          for (int half = 0; half < 2; ++half) {
-            const unsigned on_m = half ? N_hi : N_lo;
-            for (unsigned m = half ? sw_hi : sw_lo; m; m &= m - 1) {
-              const int p = __ffs(m) - 1 + 32 * half;
-              const bool on = (on_m >> (p & 31)) & 1u;
-              if (lane < SI4) {
-                const int q = p * SI4 + lane;
-                const int4 h = stg0[q];
-                const int4 w = on ? ((xbit ? s_Wn : s_Wp)[q]) : make_int4(0, 0, 0, 0);
-                int w5 = 0;
-                if constexpr (PACKED) w5 = on ? ((xbit ? s_W5n : s_W5p)[q]) : 0;
-                const long long A = row_part<PACKED>(h, w, w5, w2, w2_5, B0, B1, B2, B3, B4);
-                const int sg = on ? 1 : -1;
-                ph += sg * (A >> SO_SPLIT_BITS);
-                pl += sg * (int)(A & SO_SPLIT_MASK);
-              }
-              dn += on ? 1 : -1;
+          // the switching rows go SPP at a time: lane group g = lane / SI4 takes the g-th of them, its lanes the row's int4 parts
+          const unsigned swa = (sw_lo >> lane) & 1u, swb = (sw_hi >> lane) & 1u;
+          const int n_sw = __popc(sw_lo) + __popc(sw_hi);
+          if (swa) s_list[__popc(sw_lo & lt_mask)] = (unsigned char)lane;
+          if (swb) s_list[__popc(sw_lo) + __popc(sw_hi & lt_mask)] = (unsigned char)(lane + 32);
+          __syncwarp();
+          for (int base = 0; base < n_sw; base += SPP) {
+            const int i = base + site0;
+            if (lane < STRIDE && i < n_sw) {
+              const int p = s_list[i];
+              const bool on = ((p < 32 ? N_lo : N_hi) >> (p & 31)) & 1u;
+              const int q = p * SI4 + part;
+              const int4 h = stg0[q];
+              const int wi = (on ? dir_off : zero_off) + q;
+              const int4 w = s_Wp[wi];
+              int w5 = 0;
+              if constexpr (PACKED) w5 = s_W5p[wi];
+              const long long A = row_part<PACKED>(h, w, w5, w2, w2_5, B0, B1, B2, B3, B4);
+              const int sg = on ? 1 : -1;
+              ph += sg * (A >> SO_SPLIT_BITS);
+              pl += sg * (int)(A & SO_SPLIT_MASK);
             }
           }
+          dn = __popc(N_lo & sw_lo) + __popc(N_hi & sw_hi) - __popc(A_lo & sw_lo) - __popc(A_hi & sw_hi);
+          __syncwarp();
           int l0 = (int)(ph & 0x1fffff), l1 = (int)((ph >> 21) & 0x1fffff), l2 = (int)(ph >> 42);
           l0 = __reduce_add_sync(SO_FULL, l0);
           l1 = __reduce_add_sync(SO_FULL, l1);
@@ -466,9 +492,16 @@ __global__ void __launch_bounds__(NW * 32, 2)
               stg[STRIDE * it] = h;
             }
           }
-          // the rows that walked get their new record (path positions + gate); the others' paths do not read f
-          if (ta) stg0[QA + lane] = make_int4((int)na.x, (int)na.y, 0, 0);
-          if (tb) stg0[QA + lane + 32] = make_int4((int)nb.x, (int)nb.y, 0, 0);
+          // the rows that walked get their new record (path positions + gate) from a marking walk of the new structure (the
+          // patch is still the flipped one); the other rows' paths do not read f
+          if (ta) {
+            const uint2 m = walk_mark_cold(tree, s_patch, pa1, pa2);
+            stg0[QA + lane] = make_int4((int)m.x, (int)m.y, 0, 0);
+          }
+          if (tb) {
+            const uint2 m = walk_mark_cold(tree, s_patch, pb1, pb2);
+            stg0[QA + lane + 32] = make_int4((int)m.x, (int)m.y, 0, 0);
+          }
           fence_async_smem();
           bulk_wait_all();
           __syncwarp();
@@ -537,7 +570,7 @@ static size_t gated_smem_bytes(int Q, int K, int W, int nw, bool packed, int tre
   size_t b = ((size_t)nw * 3 * st + 3 * tab + 8) * 16;
   b += (((size_t)nw * (W + 1) + 3) & ~(size_t)3) * 4;
   if (packed) b += 3 * tab * 4;
-  b += (size_t)nw * 32 * 4;
+  b += (size_t)nw * 64 * 4;
   b += (size_t)tree_nodes * 8;
   return b + 16;
 }
