@@ -274,6 +274,37 @@ def other_configs():
             "value": st["flips"] / (st["kernel_ms"] * 1e-3), "unit": UNIT, "kernel": st["kernel"], "ms": st["kernel_ms"],
             "accept_fraction": st["accepted"] / st["flips"]}
         ch.close()
+    # the reference's surrogate is gated (OML/train_surrogate.py:34-54); the headline shape with a tree gate on the 7x7 window
+    d96 = 96
+    lat96 = engine.Lattice(d96, "NH3", device=torch.cuda.current_device())
+    off7 = engine.local_offsets(3)
+    W1l, b1l, w2l, b2l = glorot_mlp(off7, H, 0)
+    rng7 = np.random.default_rng(0)
+
+    def node7(level, t):
+        i = len(t["feature"])
+        for k, v in (("feature", -2), ("thr", 0.0), ("left", -1), ("right", -1), ("active", int(rng7.random() < 0.6))):
+            t[k].append(v)
+        if level < depth:
+            t["feature"][i], t["thr"][i] = int(rng7.integers(0, 49)), 0.5
+            t["left"][i] = node7(level + 1, t)
+            t["right"][i] = node7(level + 1, t)
+        return i
+    t7 = dict(feature=[], thr=[], left=[], right=[], active=[])
+    node7(0, t7)
+    tree7 = dict(feature=np.array(t7["feature"], np.int32), thr=np.array(t7["thr"]), left=np.array(t7["left"], np.int32),
+                 right=np.array(t7["right"], np.int32), active=np.array(t7["active"], np.uint8))
+    tab = engine.SurrogateTables(lat96, off7, W1l, b1l, w2l, b2l, tree=tree7, compact=True)
+    ch = engine.Chains(lat96, 16384)
+    ch.randomize(seed=1234, coverage=0.5)
+    ch.attach(tab)
+    temps = exp_schedule(T0, 3 * d96 * d96)
+    for i in range(3):
+        st = ch.anneal(temps[i * d96 * d96:(i + 1) * d96 * d96], step0=i * d96 * d96, seed=5)
+    out["96x96, 16384 chains, 7x7 window WITH a depth-8 tree gate, 24-bit packed state, third sweep"] = {
+        "value": st["flips"] / (st["kernel_ms"] * 1e-3), "unit": UNIT, "kernel": st["kernel"], "ms": st["kernel_ms"],
+        "accept_fraction": st["accepted"] / st["flips"]}
+    ch.close()
     n = 1 << 20
     cov = rng.random((n, 1))
     bits = engine.pack_bits((rng.random((n, N)) < cov).astype(np.uint8))

@@ -84,8 +84,16 @@ __device__ __noinline__ uint2 walk_site_cold(const uint2 *tree, const uint32_t *
 __device__ __forceinline__ unsigned extract_bits(const uint32_t *bits, int s, int n) {
   return __funnelshift_r(bits[s >> 5], bits[(s >> 5) + 1], s & 31) & ((1u << n) - 1u);
 }
+// the common case, a patch no wider than the lattice: one or two pieces, and the flipped site appears exactly once (column L - 1
+// of the centre row, toggled by the caller)
+__device__ __forceinline__ unsigned patch_row_narrow(const uint32_t *bits, int d, int y, int x0, int PW) {
+  const int n1 = min(PW, d - x0);
+  unsigned r = extract_bits(bits, y * d + x0, n1);
+  if (n1 < PW) r |= extract_bits(bits, y * d, PW - n1) << n1;
+  return r;
+}
 // row `y` of the patch: PW sites from column x0 on, cyclic, with site (f1, f2) read inverted wherever it appears
-__device__ __forceinline__ unsigned patch_row(const uint32_t *bits, int d, int y, int x0, int PW, int f1, int f2) {
+__device__ __noinline__ unsigned patch_row(const uint32_t *bits, int d, int y, int x0, int PW, int f1, int f2) {
   unsigned r = 0;
   int j = 0, x = x0;
   while (j < PW) {
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int Wpad = P.W + 1;
   // shared layout: [per warp: STAGES stages of (state Q | pad to 128 B | records K | the stage's mbarrier | padding)]
   // [+W][-W][zero W: tab_i4 int4 each][w2: 8 int4][per warp: bits W + 1][fifth weights +, -, zero: tab_i4 ints each (PACKED)]
-  // [per warp: patch 32 words | 64 + 64 bytes of lists][tree]
+  // [per warp: patch 32 words | list 64 x u16 | results 64 bytes][tree]
   unsigned char *s_stage = s_raw + (size_t)warp * STAGES * stage_i4 * 16;
   int4 *s_Wp = (int4 *)s_raw + (size_t)NW * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + tab_i4;
@@ -162,9 +170,10 @@ __global__ void __launch_bounds__(NW * 32, 2)
   int *s_W5p = (int *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * Wpad + 3) & ~(size_t)3));
   int *s_W5n = s_W5p + (PACKED ? tab_i4 : 0);
   int *s_W5z = s_W5n + (PACKED ? tab_i4 : 0);
-  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 64;       // patch rows, then two byte lists
-  unsigned char *s_list = (unsigned char *)(s_patch + 32), *s_res = s_list + 64;
-  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 64);
+  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 96;       // 32 patch rows, 64 list entries, 64 results
+  unsigned short *s_list = (unsigned short *)(s_patch + 32);
+  unsigned char *s_res = (unsigned char *)(s_list + 64);
+  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 96);
   const uint2 *tree = wg.tree_smem ? s_tree_buf : wg.tree;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   for (int q = threadIdx.x; q < tab_i4; q += blockDim.x) {
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const bool record = P.accept_out != nullptr;
   const int n_steps = (int)P.n_steps;
   const int PW = 2 * gL - 1, PH = 2 * gseg - 1;
+  const bool narrow = PW <= d && PH <= d;          // the patch holds every site at most once
   // the two window positions of this lane (rounds 0 and 1 of the gate pass) and their window coordinates
   const int pa2 = lane / gL, pa1 = lane - pa2 * gL;
   const int pb2 = (lane + 32) / gL, pb1 = (lane + 32) - pb2 * gL;
@@ -327,15 +337,19 @@ __global__ void __launch_bounds__(NW * 32, 2)
         const int n_walk = __popc(walk_a) + __popc(walk_b);
         if (n_walk) {
           // the rows to walk (about depth / K of the window) are compacted onto the first lanes: one round of walks
-          if (lane < PH) s_patch[lane] = patch_row(s_bits, d, wrap(f2 - (gseg - 1) + lane, d), wrap(f1 - (gL - 1), d), PW, f1, f2);
-          if (ta) s_list[__popc(walk_a & lt_mask)] = (unsigned char)lane;
-          if (tb) s_list[__popc(walk_a) + __popc(walk_b & lt_mask)] = (unsigned char)(lane + 32);
+          if (lane < PH) {
+            const int y = wrap(f2 - (gseg - 1) + lane, d), x0 = wrap(f1 - (gL - 1), d);
+            s_patch[lane] = narrow ? patch_row_narrow(s_bits, d, y, x0, PW) ^ ((lane == gseg - 1 ? 1u : 0u) << (gL - 1))
+                                   : patch_row(s_bits, d, y, x0, PW, f1, f2);
+          }
+          if (ta) s_list[__popc(walk_a & lt_mask)] = (unsigned short)(lane | pa1 << 6 | pa2 << 10);
+          if (tb) s_list[__popc(walk_a) + __popc(walk_b & lt_mask)] = (unsigned short)((lane + 32) | pb1 << 6 | pb2 << 10);
           __syncwarp();
           for (int base = 0; base < n_walk; base += 32) {
             if (base + lane < n_walk) {
-              const int p = s_list[base + lane];
-              const int p2 = p / gL, p1 = p - p2 * gL;
-              s_res[p] = (unsigned char)(wg.tree_smem ? walk_gate(s_tree_buf, s_patch, p1, p2) : walk_gate(wg.tree, s_patch, p1, p2));
+              const int e = s_list[base + lane];      // position | p1 << 6 | p2 << 10
+              const int p1 = (e >> 6) & 15, p2 = e >> 10;
+              s_res[e & 63] = (unsigned char)(wg.tree_smem ? walk_gate(s_tree_buf, s_patch, p1, p2) : walk_gate(wg.tree, s_patch, p1, p2));
             }
           }
           __syncwarp();
@@ -412,8 +426,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
           // the switching rows go SPP at a time: lane group g = lane / SI4 takes the g-th of them, its lanes the row's int4 parts
           const unsigned swa = (sw_lo >> lane) & 1u, swb = (sw_hi >> lane) & 1u;
           const int n_sw = __popc(sw_lo) + __popc(sw_hi);
-          if (swa) s_list[__popc(sw_lo & lt_mask)] = (unsigned char)lane;
-          if (swb) s_list[__popc(sw_lo) + __popc(sw_hi & lt_mask)] = (unsigned char)(lane + 32);
+          if (swa) s_list[__popc(sw_lo & lt_mask)] = (unsigned short)lane;
+          if (swb) s_list[__popc(sw_lo) + __popc(sw_hi & lt_mask)] = (unsigned short)(lane + 32);
           __syncwarp();
           for (int base = 0; base < n_sw; base += SPP) {
             const int i = base + site0;
@@ -570,7 +584,7 @@ static size_t gated_smem_bytes(int Q, int K, int W, int nw, bool packed, int tre
   size_t b = ((size_t)nw * 3 * st + 3 * tab + 8) * 16;
   b += (((size_t)nw * (W + 1) + 3) & ~(size_t)3) * 4;
   if (packed) b += 3 * tab * 4;
-  b += (size_t)nw * 64 * 4;
+  b += (size_t)nw * 96 * 4;
   b += (size_t)tree_nodes * 8;
   return b + 16;
 }
