@@ -507,8 +507,15 @@ def run_gpu(a):
                      "traffic": traffic, "kernel": kernel_name,
                      "bytes_per_flip": b_alg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                      "launch_ms": kern_ms / a.steps,
-                     "note": "achieved / frac count SURVEY 8(d)'s algorithmic bytes (4*K*H*(1+a) + 15 + 4a: an int32 state)"},
+                     "note": "achieved / frac count SURVEY 8(d)'s algorithmic bytes (4*K*H*(1+a) + 15 + 4a: an int32 state); "
+                             "the packed state moves fewer bytes than that, so frac can exceed 1 -- packed_state and dram "
+                             "give the rate in the bytes of the layout in use and in measured DRAM bytes"},
     }
+    if traffic:
+        # measured DRAM bytes of one launch (ncu capture of this command, profiles/) over the launch time measured HERE
+        line["roofline"]["dram"] = {"achieved": traffic / (kern_s / a.steps) / 1e9, "frac": traffic / (kern_s / a.steps) / 1e9 / peak,
+                                    "unit": "GB/s", "what": "roofline.traffic / roofline.launch_ms: the DRAM the kernel actually "
+                                                            "moves, as a fraction of the measured copy peak"}
     if a.compact:
         # the kernel actually moves 64 instead of 80 bytes per site: the same rate in bytes of the packed layout
         b_packed = 64.0 * K_WIN * (1.0 + acc_frac) + 15.0 + 4.0 * acc_frac
