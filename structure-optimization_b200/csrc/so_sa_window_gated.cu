@@ -138,11 +138,12 @@ __device__ __forceinline__ long long row_part(const int4 h, const int4 w, int w5
 
 // NW warps per CTA, 2 CTAs per SM.  HP4 = 5 (17..20 hidden units) only: PACKED = the 24-bit state (4 int4 per site, slots of five
 // values), else int32 (5 int4 per site).
-template <int NSLOTS, bool PACKED, int NW>
+// STAGES = 2: a gated step takes ~3 us per warp, far longer than an HBM round trip, so ONE window in flight per warp hides the
+// latency and the shared memory of the third stage buys more warps per SM (the open kernel's step is 4 x shorter: three stages).
+template <int NSLOTS, bool PACKED, int NW, int STAGES>
 __global__ void __launch_bounds__(NW * 32, 2)
     sa_window_gated_kernel(SaParams P, WinGeom g, WinGate wg, const int4 *__restrict__ Wst,
                            const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_meta) {
-  constexpr int STAGES = 3;
   constexpr int HP4 = 5;
   constexpr int SI4 = PACKED ? 4 : HP4;
   constexpr int STRIDE = (32 / SI4) * SI4;
@@ -544,15 +545,19 @@ __global__ void __launch_bounds__(NW * 32, 2)
           nact += dn;
           ++n_acc;
         }
-        hist1 = hist0;
+        hist1 = STAGES == 3 ? hist0 : -1;            // a window is prefetched STAGES - 1 steps ahead: that many flips can outdate it
         hist0 = accept ? fp : -1;
         if (record) {
           if (lane == 0) P.accept_out[c * P.n_steps + s] = accept ? 1 : 0;
         }
         __syncwarp();
       }
-      f_b = f_a; thr_b = thr_a;
-      f_a = f_q; thr_a = thr_q;
+      if constexpr (STAGES == 3) {
+        f_b = f_a; thr_b = thr_a;
+        f_a = f_q; thr_a = thr_q;
+      } else {
+        f_b = f_q; thr_b = thr_q;
+      }
       p_off = c_off;
     }
     bulk_wait_all();
@@ -579,9 +584,11 @@ static int gated_stage_i4(int Q, int K) { return (((Q + 7) & ~7) + K + 1 + 7) & 
 
 static int gated_tab_i4(int Q) { return (Q + 3 + 7) & ~7; }
 
+constexpr int kGatedStages = 2;
+
 static size_t gated_smem_bytes(int Q, int K, int W, int nw, bool packed, int tree_nodes) {
   const size_t st = gated_stage_i4(Q, K), tab = gated_tab_i4(Q);
-  size_t b = ((size_t)nw * 3 * st + 3 * tab + 8) * 16;
+  size_t b = ((size_t)nw * kGatedStages * st + 3 * tab + 8) * 16;
   b += (((size_t)nw * (W + 1) + 3) & ~(size_t)3) * 4;
   if (packed) b += 3 * tab * 4;
   b += (size_t)nw * 96 * 4;
@@ -592,7 +599,7 @@ static size_t gated_smem_bytes(int Q, int K, int W, int nw, bool packed, int tre
 template <int NSLOTS, bool PACKED, int NW>
 static int launch_gated(const so_chains *c, const SaParams &P, const WinGeom &g, const WinGate &wg, size_t smem, int blocks,
                         cudaStream_t st) {
-  auto kern = sa_window_gated_kernel<NSLOTS, PACKED, NW>;
+  auto kern = sa_window_gated_kernel<NSLOTS, PACKED, NW, kGatedStages>;
   SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, NW * 32, smem, st>>>(P, g, wg, (const int4 *)(PACKED ? c->sur->Wst24_dev : c->sur->Wst_dev), c->tmap,
                                       c->tmap_meta);
