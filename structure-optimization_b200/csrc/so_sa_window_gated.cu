@@ -649,6 +649,8 @@ int so_launch_anneal_window_gated(const so_chains *c, const SaParams &P, cudaStr
   wg.build = build_records ? 1 : 0;
   // warps per CTA: as many as two CTAs per SM allow (8 .. 4); the tree rides in shared memory when it still fits
   int nw = 8;
+  // (9 or 10 warps per CTA fit the shared memory but not the register file: 96 registers per thread, 100+ bytes of spills,
+  // 7.57e8 -> 7.07e8 / 7.25e8 flip-evaluations/s)
   while (nw > 4 && gated_smem_bytes(Q, s->K, P.W, nw, packed, 0) > kCtaSmemLimit) --nw;
   wg.tree_smem = gated_smem_bytes(Q, s->K, P.W, nw, packed, s->n_tree) <= kCtaSmemLimit ? 1 : 0;
   if (!wg.tree_smem && nw > 6 && gated_smem_bytes(Q, s->K, P.W, nw - 1, packed, s->n_tree) <= kCtaSmemLimit) {
