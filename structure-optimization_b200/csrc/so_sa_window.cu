@@ -11,7 +11,8 @@
 //     Rare hazards (the window of a prefetched step overlaps a flip accepted after the prefetch was issued, or a
 //     store still in flight) are detected exactly and resolved by draining the stores and re-fetching;
 //   * Philox and the injected-sequence loads are evaluated lane-parallel for 32 steps at a time; the warp sum uses
-//     three REDUX.SUM on 21-bit limbs; exp() runs in fp64 only when an fp32 pre-filter cannot decide.
+//     three REDUX.SUM on 21-bit limbs; the decision is an fp32 comparison with a per-draw threshold thr = min(T ln u, 0)
+//     computed in fp64 with the draws, the fp64 rule runs only when the two sides are within 1e-5 of each other.
 #include "so_window_common.cuh"
 #include "so_types.cuh"
 #include <stdlib.h>

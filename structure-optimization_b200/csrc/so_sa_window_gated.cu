@@ -221,11 +221,19 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int PW = 2 * gL - 1, PH = 2 * gseg - 1;
   const bool narrow = PW <= d && PH <= d;          // the patch holds every site at most once
   // the two window positions of this lane (rounds 0 and 1 of the gate pass) and their window coordinates
-  const int pa2 = lane / gL, pa1 = lane - pa2 * gL;
-  const int pb2 = (lane + 32) / gL, pb1 = (lane + 32) - pb2 * gL;
+  // ... packed into ONE opaque register (position | p1 << 6 | p2 << 10, for lane and lane + 32): left visible, the compiler
+  // rematerialises the two divisions inside the step loop to save registers (28 instructions per step)
+  unsigned ent;
+  {
+    const int pa2 = lane / gL, pa1 = lane - pa2 * gL;
+    const int pb2 = (lane + 32) / gL, pb1 = (lane + 32) - pb2 * gL;
+    ent = (unsigned)(lane | pa1 << 6 | pa2 << 10) | ((unsigned)((lane + 32) | pb1 << 6 | pb2 << 10) << 16);
+    asm volatile("" : "+r"(ent));
+  }
   const bool va = lane < K, vb = lane + 32 < K;
   const int site0 = lane / SI4;                     // window site of the lane's slot 0 (slot it: site0 + SPP * it)
-  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned lt_mask;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
   uint32_t p_off = 0, par = 1;
 
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
             s_patch[lane] = narrow ? patch_row_narrow(s_bits, d, y, x0, PW) ^ ((lane == gseg - 1 ? 1u : 0u) << (gL - 1))
                                    : patch_row(s_bits, d, y, x0, PW, f1, f2);
           }
-          if (ta) s_list[__popc(walk_a & lt_mask)] = (unsigned short)(lane | pa1 << 6 | pa2 << 10);
-          if (tb) s_list[__popc(walk_a) + __popc(walk_b & lt_mask)] = (unsigned short)((lane + 32) | pb1 << 6 | pb2 << 10);
+          if (ta) s_list[__popc(walk_a & lt_mask)] = (unsigned short)(ent & 0xffffu);
+          if (tb) s_list[__popc(walk_a) + __popc(walk_b & lt_mask)] = (unsigned short)(ent >> 16);
           __syncwarp();
           for (int base = 0; base < n_walk; base += 32) {
             if (base + lane < n_walk) {
@@ -510,11 +518,11 @@ __global__ void __launch_bounds__(NW * 32, 2)
           // the rows that walked get their new record (path positions + gate) from a marking walk of the new structure (the
           // patch is still the flipped one); the other rows' paths do not read f
           if (ta) {
-            const uint2 m = walk_mark_cold(tree, s_patch, pa1, pa2);
+            const uint2 m = walk_mark_cold(tree, s_patch, (ent >> 6) & 15, (ent >> 10) & 15);
             stg0[QA + lane] = make_int4((int)m.x, (int)m.y, 0, 0);
           }
           if (tb) {
-            const uint2 m = walk_mark_cold(tree, s_patch, pb1, pb2);
+            const uint2 m = walk_mark_cold(tree, s_patch, (ent >> 22) & 15, (ent >> 26) & 15);
             stg0[QA + lane + 32] = make_int4((int)m.x, (int)m.y, 0, 0);
           }
           fence_async_smem();
