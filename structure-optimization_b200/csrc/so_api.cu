@@ -931,7 +931,14 @@ int so_anneal(so_chains *c, const so_anneal_args *a, so_anneal_stats *stats) {
     for (int k = 0; full && k < su->K; ++k)
       full = su->offs_host[k] == (int32_t)(((k / L->d) << 16) | (k % L->d));
     const char *e2 = getenv("SO_RES_ACTIVE_LIST");
-    if (full && !(e2 && e2[0] == '0')) P.variant_flags |= 2;
+    if (full && !(e2 && e2[0] == '0')) {
+      P.variant_flags |= 2;
+      // ... then a lane per whole row wins the difference pass too (golden surrogate +5 %, 60 % active rows +17 %)
+      if (!e) P.variant_flags |= 1;
+      // (tried and dropped: walks on a doubled bit plane + look-up tables instead of wrap() arithmetic remove ~250 of the
+      //  1,310 instructions of a gated step and change nothing -- 5.26e8 vs 5.39e8: with one warp per chain the step is a
+      //  serial chain of phases, 5.7 cycles per instruction at 16 warps per SM, not an issue-bound loop)
+    }
   }
   P.d = L->d; P.N = L->N; P.W = L->W; P.n_chains = c->n_chains;
   P.bits = c->bits_dev; P.hq = c->hq_dev; P.hi = c->hi_dev; P.lo = c->lo_dev; P.nact = c->nact_dev;
