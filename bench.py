@@ -181,7 +181,7 @@ def workload_config(a, cores_note=None):
            "lattice": "%dx%d" % (a.d, a.d), "chains_per_gpu": a.chains, "descriptor": "local7x7", "hidden": H,
            "step": "one sweep = %d Metropolis steps per chain" % (a.sweep_steps if a.sweep_steps > 0 else a.d * a.d),
            "l2_policy": "working set (%.1f GB of per-chain state) >> 126 MB L2; no flush needed" % (
-               a.chains * a.d * a.d * H * 4 / 1e9),
+               a.chains * a.d * a.d * (64 if a.compact else H * 4) / 1e9),
            "rng": "Philox4x32-10, key=seed, counter=(step, chain)",
            "state": ("first-layer state packed to 24 bits per hidden unit, 64 B per site (scores within 1e-5 of fp64)"
                      if a.compact else "first-layer state int32, 80 B per site")}
