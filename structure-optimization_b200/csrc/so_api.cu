@@ -255,7 +255,16 @@ static int rescore(so_chains *c, int64_t chain0, int64_t n) {
   NvtxRange nvtx_range("state build (first-layer state + objective sums from the bits)");
   const so_lattice *L = c->lat;
   if (c->sur->compact) {
-    // the scorers write int32 [site][20]; slabs of it are packed to 24 bits / 64 bytes per site (so_sa_window.cu)
+    // the tensor-core scorer packs its rows to 24 bits / 64 bytes per site in the epilogue (SO_SCORE_TC=0 / SO_SCORE_PACK=0 keep
+    // the two-pass build below: both give the same bytes, tests compare them)
+    {
+      const char *e1 = getenv("SO_SCORE_TC"), *e2 = getenv("SO_SCORE_PACK");
+      if (c->sur->tc_ok && !(e1 && e1[0] == '0') && !(e2 && e2[0] == '0'))
+        return so_launch_score_tc(L, c->sur, c->bits_dev + chain0 * L->W, n,
+                                  (int32_t *)((char *)c->hq_dev + (size_t)chain0 * L->N * 64), c->hi_dev + chain0,
+                                  c->lo_dev + chain0, c->nact_dev + chain0, c->stream, 1);
+    }
+    // otherwise the scorers write int32 [site][20]; slabs of it are packed to 24 bits / 64 bytes per site (so_sa_window.cu)
     const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n, (1LL << 30) / ((int64_t)L->N * 80)));
     if ((int64_t)c->tmp_hq_chains < slab) {
       cudaFree(c->tmp_hq_dev);

@@ -183,7 +183,7 @@ int so_launch_score(const so_lattice *lat, const so_surrogate *s, const uint32_t
 int so_normalize_sums(long long *hi, long long *lo, int64_t n, cudaStream_t st);
 int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, int *n_mma_out);
 int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
-                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st);
+                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st, int packed_out = 0);
 int so_launch_objective(const so_surrogate *s, const long long *hi, const long long *lo, const int32_t *nact, int64_t n,
                         double *of_dev, cudaStream_t st);
 int so_launch_eval_rows(const so_surrogate *s, int64_t n_rows, const uint8_t *X_dev, uint8_t *active_dev,

@@ -75,7 +75,10 @@ template <int HP4, int NCH>
 __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restrict__ bits_all, int d, int N, int W,
                                                        long long n_chains, SurView sv, TcGeom g,
                                                        const uint4 *__restrict__ b_image, int32_t *hq_all,
-                                                       long long *hi_out, long long *lo_out, int32_t *nact_out) {
+                                                       long long *hi_out, long long *lo_out, int32_t *nact_out,
+                                                       const int32_t *__restrict__ bias24) {
+  // bias24 != null (HP4 = 5 only): hq_all is the 24-bit packed state, 64 bytes per row (so_sa_window.cu: pack24_kernel's layout);
+  // the epilogue packs the row itself and the int32 slab + pack pass of the state build disappear
   constexpr int HP = HP4 * 4;
   const int n_chunks = NCH ? NCH : g.n_chunks;
   const bool kw8 = NCH ? true : (g.kw == 8);
@@ -211,10 +214,23 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
         long long A = 0;
 #pragma unroll
         for (int j = 0; j < HP; ++j) A += (long long)w2q[j] * (long long)max(h[j], 0);
-        if (hq_all) {                                 // 80-B row stride: conflict-free 16-B shared stores
-          int4 *dst = s_out + (size_t)buf * TILE_M * HP4 + (size_t)tid * HP4;
+        if (hq_all) {
+          if (HP4 == 5 && bias24) {                   // five biased 24-bit values per int4, four int4 per row
+            int4 *dst = s_out + (size_t)buf * TILE_M * HP4 + (size_t)tid * 4;
 #pragma unroll
-          for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
+            for (int p = 0; p < 4; ++p) {
+              const unsigned v0 = (unsigned)(h[5 * p] + __ldg(bias24 + 5 * p)) & 0xffffffu,
+                             v1 = (unsigned)(h[5 * p + 1] + __ldg(bias24 + 5 * p + 1)) & 0xffffffu,
+                             v2 = (unsigned)(h[5 * p + 2] + __ldg(bias24 + 5 * p + 2)) & 0xffffffu,
+                             v3 = (unsigned)(h[5 * p + 3] + __ldg(bias24 + 5 * p + 3)) & 0xffffffu,
+                             v4 = (unsigned)(h[5 * p + 4] + __ldg(bias24 + 5 * p + 4)) & 0xffffffu;
+              dst[p] = make_int4((int)(v0 | (v1 << 24)), (int)((v1 >> 8) | (v2 << 16)), (int)((v2 >> 16) | (v3 << 8)), (int)v4);
+            }
+          } else {                                    // 80-B row stride: conflict-free 16-B shared stores
+            int4 *dst = s_out + (size_t)buf * TILE_M * HP4 + (size_t)tid * HP4;
+#pragma unroll
+            for (int p = 0; p < HP4; ++p) dst[p] = make_int4(h[4 * p], h[4 * p + 1], h[4 * p + 2], h[4 * p + 3]);
+          }
         }
         BitView bv{mybits, d, -1};
         const int gate = sv.gated ? tree_gate(sv, bv, r1, r2) : 1;
@@ -244,8 +260,9 @@ __global__ void __launch_bounds__(128) score_tc_kernel(const uint32_t *__restric
       __syncthreads();
       if (tid == 0) {
         const int rows = (int)min((long long)TILE_M, total_rows - G0);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(hq_all + (size_t)G0 * HP),
-                     "r"(smem_u32(s_out + (size_t)buf * TILE_M * HP4)), "r"((uint32_t)(rows * HP * 4))
+        const uint32_t row_bytes = (HP4 == 5 && bias24) ? 64u : (uint32_t)(HP * 4);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((char *)hq_all + (size_t)G0 * row_bytes),
+                     "r"(smem_u32(s_out + (size_t)buf * TILE_M * HP4)), "r"((uint32_t)rows * row_bytes)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the other buffer is free again
@@ -291,8 +308,9 @@ int so_build_tc_image(const so_surrogate *s, std::vector<unsigned char> &img, in
 }
 
 int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint32_t *bits_dev, int64_t n, int32_t *hq_dev,
-                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st) {
+                       long long *hi, long long *lo, int32_t *nact, cudaStream_t st, int packed_out) {
   if (n == 0) return SO_OK;
+  SO_REQUIRE(!packed_out || (s->compact && s->HP4 == 5 && s->bias24_dev), "packed output needs a compact surrogate");
   TcGeom g;
   g.a1 = s->win_a1; g.a2 = s->win_a2; g.L = s->win_b1 - s->win_a1 + 1; g.n_seg = s->win_b2 - s->win_a2 + 1;
   g.kw = g.L <= 8 ? 8 : 16;
@@ -314,7 +332,7 @@ int so_launch_score_tc(const so_lattice *lat, const so_surrogate *s, const uint3
     auto kern = (g.kw == 8 && g.n_chunks == 4) ? score_tc_kernel<V, 4> : score_tc_kernel<V, 0>;                    \
     SO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
     kern<<<blocks, 128, smem, st>>>(bits_dev, lat->d, lat->N, lat->W, n, sv, g, (const uint4 *)s->tc_image_dev,    \
-                                    hq_dev, hi, lo, nact);                                                         \
+                                    hq_dev, hi, lo, nact, packed_out ? s->bias24_dev : nullptr);                   \
   } break;
     SO_TC_CASE(1) SO_TC_CASE(2) SO_TC_CASE(3) SO_TC_CASE(4) SO_TC_CASE(5) SO_TC_CASE(6) SO_TC_CASE(7) SO_TC_CASE(8)
 #undef SO_TC_CASE

@@ -647,6 +647,15 @@ def test_compact_state_window_kernel(eng, d, n, steps, T0):
     ch.attach(tab)
     hq0, _ = S.preact_fixed(p, q, x0[3], d)
     assert (ch.preact(3)[:, :20] == hq0[:, :20]).all()                   # pack / unpack round trip of the state build
+    # the tensor-core scorer packs in its epilogue; the two-pass build (int32 slab + pack kernel) must give the same state
+    import os
+    of_fused, pre_fused = ch.objective(), ch.preact(n - 1)
+    os.environ["SO_SCORE_PACK"] = "0"
+    try:
+        assert (ch.score() == of_fused).all() and (ch.preact(n - 1) == pre_fused).all()
+    finally:
+        del os.environ["SO_SCORE_PACK"]
+    assert (ch.score() == of_fused).all() and (ch.preact(n - 1) == pre_fused).all()
     for c in range(0, n, max(1, n // 8)):
         ref = S.eval_rate_fp64(p, L.descriptor_rows(x0[c], p.offsets, d))
         assert abs(ch.objective(c, 1)[0] - ref) <= 1e-5 * max(abs(ref), 1e-12)
