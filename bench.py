@@ -400,7 +400,12 @@ def run_gpu(a):
             if pt is not None:
                 pt.round(s, t_ref=T0)
             if gather is not None and ((s + 1) % gather_every == 0 or s == total_sweeps - 1):
-                gather.gather()
+                # every gather but the last overlaps the next sweep (side stream); the last one is waited for and timed here
+                if pt is None and s != total_sweeps - 1 and s != a.warmup - 1:
+                    gather.gather_async()
+                else:
+                    gather.finish()
+                    gather.gather()
                 n_gathers[0] += 1
             ev1.record()
             ev1.synchronize()

@@ -69,6 +69,44 @@ class BestGather(object):
         self.rec = torch.zeros(record_bytes(self.words), dtype=torch.uint8, device=dev)
         self.all = torch.zeros((self.world, record_bytes(self.words)), dtype=torch.uint8, device=dev)
         self.best = (-math.inf, -1, None)        # best-so-far over all gathers
+        # overlapped form (gather_async / finish): a side stream for the collective and the copy to a pinned host buffer
+        self.side = torch.cuda.Stream(device=dev)
+        self.host = torch.zeros((self.world, record_bytes(self.words)), dtype=torch.uint8).pin_memory()
+        self.done = torch.cuda.Event()
+        self.pending = False
+
+    def gather_async(self):
+        """The same exchange off the critical path (collective on a side stream): the arg-max kernel runs now
+        (it reads the chains, so the next sweep must not start before it: the host waits for it, a few tens of us), the
+        all-gather and the device-to-host copy are queued on the side stream and overlap the next sweep; finish() returns the
+        round's global best.  Rank skew is absorbed by the side stream instead of stalling the sweep."""
+        torch = self.torch
+        if self.pending:
+            self.finish()
+        with torch.cuda.stream(self.side):
+            B.check(self.ch.lib.so_best_record_dev(self.ch.h, self.chain_id0, C.c_void_p(self.rec.data_ptr()),
+                                                   C.c_void_p(self.side.cuda_stream)))
+            self.side.synchronize()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.all.view(-1), self.rec, group=self.group)
+            else:
+                self.all[0].copy_(self.rec)
+            self.host.copy_(self.all, non_blocking=True)
+            self.done.record(self.side)
+        self.pending = True
+
+    def finish(self):
+        """Wait for the pending gather_async() and fold its result into the best-so-far; returns the round's global best."""
+        if not self.pending:
+            return None
+        self.done.synchronize()
+        self.pending = False
+        of, cid, bits = parse_records(self.host.numpy(), self.words)
+        cur = pick_best(of, cid, bits)
+        if cur[0] > self.best[0]:
+            self.best = cur
+        return cur
 
     def gather(self):
         """Arg-max kernel writes straight into the NCCL send buffer; returns the global best of this round."""
