@@ -266,11 +266,12 @@ def test_sa_window_hot_chains(eng, d, variant):
     assert r["acc"].mean() > 0.1
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4])
-def test_sa_window_many_chains(eng, variant):
-    """More chains than resident warps: dynamic chain hand-out + stage/mbarrier reuse across chains."""
+@pytest.mark.parametrize("variant,steps", [(0, 70), (3, 70), (3, 71), (3, 72), (4, 70)])
+def test_sa_window_many_chains(eng, variant, steps):
+    """More chains than resident warps: dynamic chain hand-out + stage/mbarrier reuse across chains (the ring of stages is
+    continuous over the chains of a warp: all three step counts modulo the number of stages)."""
     p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=41)
-    _run_sa(eng, 12, p, n_chains=5000, steps=70, seed=51, T0=0.5, check_chains=range(0, 5000, 97), cooling="const",
+    _run_sa(eng, 12, p, n_chains=5000, steps=steps, seed=51, T0=0.5, check_chains=range(0, 5000, 97), cooling="const",
             variant=variant)
 
 
@@ -380,6 +381,17 @@ def test_sa_window_gated_kernel(eng, d, n, steps, T0, depth, compact):
     o64 = c_oracle.anneal_fp64_many(p, d, x0[:m], temps, prop[:m], u[:m], margin_thr=1e-9)
     ok = o64["n_below"] == 0
     assert (acc2[:m].astype(bool)[ok] == o64["accept"][ok]).all() and ok.mean() > 0.9
+
+
+def test_sa_window_gated_many_chains(eng):
+    """More chains than resident warps on the gated window kernel: dynamic chain hand-out, the two-stage ring and its mbarrier
+    phases carried from one chain of a warp to the next, records rebuilt per chain."""
+    p = S.SurrogateParams.random_init(L.local_offsets(3), H=20, seed=141)
+    p.tree = _random_tree(49, 7, seed=142)
+    for steps in (70, 71):                       # even and odd step counts: both ring positions at the hand-over
+        r = _run_sa(eng, 12, p, n_chains=6000, steps=steps, seed=151 + steps, T0=0.5, check_chains=range(0, 6000, 113),
+                    cooling="const", variant=3)
+        assert r["stats"]["kernel"] == "sa_window_gated_kernel"
 
 
 @pytest.mark.parametrize("variant", [4, 5])
