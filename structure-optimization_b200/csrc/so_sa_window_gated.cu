@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const float k_f = (float)(P.sv.y_scale * P.sv.c);
   const int fast_ok = !P.exact_guard && fabsf(k_f) > 1e-30f && fabsf(k_f) < 1e30f;
   const int gb1 = g.b1, gb2 = g.b2, gL = g.L, gseg = g.n_seg;
-  const unsigned lim1 = g.use_tma ? (unsigned)(d - gL + 1) : 0u, lim2 = g.use_tma ? (unsigned)(d - gseg + 1) : 0u;
+  unsigned lim1 = g.use_tma ? (unsigned)(d - gL + 1) : 0u, lim2 = g.use_tma ? (unsigned)(d - gseg + 1) : 0u;
+  asm volatile("" : "+r"(lim1), "+r"(lim2));      // (opaque: otherwise recomputed from the parameters inside the step loop)
   const bool record = P.accept_out != nullptr;
   const int n_steps = (int)P.n_steps;
   const int PW = 2 * gL - 1, PH = 2 * gseg - 1;
@@ -245,8 +246,10 @@ __global__ void __launch_bounds__(NW * 32, 2)
     uint32_t *bits_g = P.bits + c * P.W;
     for (int w = lane; w < P.W; w += 32) s_bits[w] = bits_g[w];
     if (lane == 0) s_bits[P.W] = 0u;
-    int4 *hq = (int4 *)P.hq + c * (long long)P.N * SI4;
-    int4 *meta = wg.meta + c * (long long)P.N;
+    // (state and records of the chain are addressed through the tensor maps; the plain pointers are formed where the cold
+    //  paths need them, not once per step)
+#define SO_WG_HQ ((int4 *)P.hq + c * (long long)P.N * SI4)
+#define SO_WG_META (wg.meta + c * (long long)P.N)
     long long hi = P.hi[c], lo = P.lo[c];
     int nact = P.nact[c];
     const double tsc = P.tscale[c];
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
         if (r < P.N) {
           const int r2 = r / d;
           const uint2 m = walk_site_cold(tree, s_bits, d, r - r2 * d, r2, wg.a1, wg.a2);
-          meta[r] = make_int4((int)m.x, (int)m.y, 0, 0);
+          SO_WG_META[r] = make_int4((int)m.x, (int)m.y, 0, 0);
         }
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -308,8 +311,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
           } else {
             if (lane == 0) mbar_expect_tx(bar, tx_bytes);
             __syncwarp();
-            boundary_loads_cold(hq, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, SI4, lane);
-            boundary_loads_cold(meta, dst + meta_off, bar, q1, q2, gb1, gb2, gL, gseg, d, 1, lane);
+            boundary_loads_cold(SO_WG_HQ, dst, bar, q1, q2, gb1, gb2, gL, gseg, d, SI4, lane);
+            boundary_loads_cold(SO_WG_META, dst + meta_off, bar, q1, q2, gb1, gb2, gL, gseg, d, 1, lane);
           }
         }
       }
@@ -332,8 +335,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
           bulk_wait_all();
           pend_f = -1;
           __syncwarp();
-          reload_window_cold(stg0, hq, f1, f2, gb1, gb2, gL, Q, d, SI4, lane);
-          reload_window_cold(stg0 + QA, meta, f1, f2, gb1, gb2, gL, K, d, 1, lane);
+          reload_window_cold(stg0, SO_WG_HQ, f1, f2, gb1, gb2, gL, Q, d, SI4, lane);
+          reload_window_cold(stg0 + QA, SO_WG_META, f1, f2, gb1, gb2, gL, K, d, 1, lane);
           __syncwarp();
         }
         // ---- gates: g0 from the records, g1 by walking the rows whose path tests f -----------------------------
@@ -537,8 +540,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
                 tma_store_3d(&tmap_meta, (f1 - gb1) * 4, f2 - gb2, (int)c, src + meta_off);
               }
             } else {
-              boundary_stores_cold(hq, src, f1, f2, gb1, gb2, gL, gseg, d, SI4, lane);
-              boundary_stores_cold(meta, src + meta_off, f1, f2, gb1, gb2, gL, gseg, d, 1, lane);
+              boundary_stores_cold(SO_WG_HQ, src, f1, f2, gb1, gb2, gL, gseg, d, SI4, lane);
+              boundary_stores_cold(SO_WG_META, src + meta_off, f1, f2, gb1, gb2, gL, gseg, d, 1, lane);
             }
             if (lane == 0 || !interior) {
               bulk_commit();
@@ -585,6 +588,8 @@ __global__ void __launch_bounds__(NW * 32, 2)
     }
     __syncwarp();
   }
+#undef SO_WG_HQ
+#undef SO_WG_META
 }
 
 // int4 per stage: state, pad to 8, records, mbarrier, pad to 8
