@@ -765,7 +765,7 @@ int so_chains_attach(so_chains *c, so_surrogate *s) {
   if (s->win_ok) {
     const int Lw = s->win_b1 - s->win_a1 + 1, nseg = s->win_b2 - s->win_a2 + 1;
     c->tmap_ok = window_tensor_map(&c->tmap, c->hq_dev, L, c->n_chains, site_words, Lw, nseg);
-    if (s->gated && s->wtree_dev && c->tmap_ok) {
+    if (s->gated && s->wtree_dev && s->HP4 == 5 && c->tmap_ok) {          // (the shapes so_window_gated_ok accepts)
       if (cudaMalloc(&c->gate_meta_dev, (size_t)c->n_chains * L->N * 16) == cudaSuccess) {
         c->tmap_meta_ok = window_tensor_map(&c->tmap_meta, c->gate_meta_dev, L, c->n_chains, 4, Lw, nseg);
       } else {
