@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NW * 32, 2)
   const int Wpad = P.W + 1;
   // shared layout: [per warp: STAGES stages of (state Q | pad to 128 B | records K | the stage's mbarrier | padding)]
   // [+W][-W][zero W: tab_i4 int4 each][w2: 8 int4][per warp: bits W + 1][fifth weights +, -, zero: tab_i4 ints each (PACKED)]
-  // [per warp: patch 32 words | list 64 x u16 | results 64 bytes][tree]
+  // [per warp: patch 32 words | two lists 64 x u16 | results 64 bytes][tree]
   unsigned char *s_stage = s_raw + (size_t)warp * STAGES * stage_i4 * 16;
   int4 *s_Wp = (int4 *)s_raw + (size_t)NW * STAGES * stage_i4;
   int4 *s_Wn = s_Wp + tab_i4;
@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(NW * 32, 2)
   int *s_W5p = (int *)((uint32_t *)(s_w2 + 8) + (((size_t)NW * Wpad + 3) & ~(size_t)3));
   int *s_W5n = s_W5p + (PACKED ? tab_i4 : 0);
   int *s_W5z = s_W5n + (PACKED ? tab_i4 : 0);
-  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 96;       // 32 patch rows, 64 list entries, 64 results
-  unsigned short *s_list = (unsigned short *)(s_patch + 32);
-  unsigned char *s_res = (unsigned char *)(s_list + 64);
-  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 96);
+  uint32_t *s_patch = (uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + warp * 128;      // 32 patch rows, 2 x 64 list entries, 64 results
+  unsigned short *s_list = (unsigned short *)(s_patch + 32), *s_swl = s_list + 64;  // rows to walk / rows that switch
+  unsigned char *s_res = (unsigned char *)(s_swl + 64);
+  uint2 *s_tree_buf = (uint2 *)((uint32_t *)(s_W5z + (PACKED ? tab_i4 : 0)) + NW * 128);
   const uint2 *tree = wg.tree_smem ? s_tree_buf : wg.tree;
   if (threadIdx.x < HP4) s_w2[threadIdx.x] = ((const int4 *)P.sv.w2q)[threadIdx.x];
   for (int q = threadIdx.x; q < tab_i4; q += blockDim.x) {
@@ -438,13 +438,13 @@ __global__ void __launch_bounds__(NW * 32, 2)
           // the switching rows go SPP at a time: lane group g = lane / SI4 takes the g-th of them, its lanes the row's int4 parts
           const unsigned swa = (sw_lo >> lane) & 1u, swb = (sw_hi >> lane) & 1u;
           const int n_sw = __popc(sw_lo) + __popc(sw_hi);
-          if (swa) s_list[__popc(sw_lo & lt_mask)] = (unsigned short)lane;
-          if (swb) s_list[__popc(sw_lo) + __popc(sw_hi & lt_mask)] = (unsigned short)(lane + 32);
+          if (swa) s_swl[__popc(sw_lo & lt_mask)] = (unsigned short)lane;
+          if (swb) s_swl[__popc(sw_lo) + __popc(sw_hi & lt_mask)] = (unsigned short)(lane + 32);
           __syncwarp();
           for (int base = 0; base < n_sw; base += SPP) {
             const int i = base + site0;
             if (lane < STRIDE && i < n_sw) {
-              const int p = s_list[i];
+              const int p = s_swl[i];
               const bool on = ((p < 32 ? N_lo : N_hi) >> (p & 31)) & 1u;
               const int q = p * SI4 + part;
               const int4 h = stg0[q];
@@ -520,13 +520,13 @@ __global__ void __launch_bounds__(NW * 32, 2)
           }
           // the rows that walked get their new record (path positions + gate) from a marking walk of the new structure (the
           // patch is still the flipped one); the other rows' paths do not read f
-          if (ta) {
-            const uint2 m = walk_mark_cold(tree, s_patch, (ent >> 6) & 15, (ent >> 10) & 15);
-            stg0[QA + lane] = make_int4((int)m.x, (int)m.y, 0, 0);
-          }
-          if (tb) {
-            const uint2 m = walk_mark_cold(tree, s_patch, (ent >> 22) & 15, (ent >> 26) & 15);
-            stg0[QA + lane + 32] = make_int4((int)m.x, (int)m.y, 0, 0);
+          // (the compacted list of the gate pass is still there: one round of marking walks, each writing its row's record)
+          for (int base = 0; base < n_walk; base += 32) {
+            if (base + lane < n_walk) {
+              const int e = s_list[base + lane];
+              const uint2 m = walk_mark_cold(tree, s_patch, (e >> 6) & 15, e >> 10);
+              stg0[QA + (e & 63)] = make_int4((int)m.x, (int)m.y, 0, 0);
+            }
           }
           fence_async_smem();
           bulk_wait_all();
@@ -604,7 +604,7 @@ static size_t gated_smem_bytes(int Q, int K, int W, int nw, bool packed, int tre
   size_t b = ((size_t)nw * kGatedStages * st + 3 * tab + 8) * 16;
   b += (((size_t)nw * (W + 1) + 3) & ~(size_t)3) * 4;
   if (packed) b += 3 * tab * 4;
-  b += (size_t)nw * 96 * 4;
+  b += (size_t)nw * 128 * 4;
   b += (size_t)tree_nodes * 8;
   return b + 16;
 }
