@@ -151,7 +151,8 @@ struct SaParams {
                                         // 4 resident warp-per-chain kernel even for few chains, 5 CTA-per-chain kernel
   unsigned long long *counters;
   uint32_t *gate_scratch;
-  int variant_flags;                    // bit 0: resident kernel takes a lane per whole row in the difference pass
+  int variant_flags;                    // bit 0: resident kernel takes a lane per whole row in the difference pass; bit 1: persistent
+                                        // list of active rows; bit 3: path index of the resident kernel in the global scratch
   int32_t *type_hist;                   // [n_chains][11] tracked type histograms (so_track_types) or null
   SurView sv;
 };
@@ -201,7 +202,8 @@ bool so_window_gated_ok(const so_chains *c);
 int so_launch_anneal_window_gated(const so_chains *c, const SaParams &P, cudaStream_t st, int build_records);
 size_t so_window_smem_bytes(int Q, int W, int stages);
 int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st);
-bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem, int min_warps_per_sm = 8);
+bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps, size_t *smem, int min_warps_per_sm = 8,
+                      int *index_global = nullptr);
 bool so_gate_index_ok(const so_surrogate *s, int N, int W);
 bool so_team_ok(const so_surrogate *s, int N, int W, long long n_chains, int n_sm);
 int so_launch_anneal_team(const so_chains *c, const SaParams &P, cudaStream_t st);

@@ -18,6 +18,7 @@
 #include "so_internal.cuh"
 #include "so_types.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #define SO_TREE_SMEM_NODES 2048
 
@@ -145,15 +146,19 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
   int32_t *s_off = (int32_t *)(s_tree_buf + n_tree);
   int4 *s_w2 = (int4 *)((unsigned char *)s_off + a16((size_t)K * 4));
   unsigned char *s_chain0 = (unsigned char *)(s_w2 + HP4);
+  // resident state with the path index in the per-warp GLOBAL scratch (variant_flags bit 3): 2.9 KB less shared memory per warp
+  // at N = K = 144 buys 16 instead of 12 warps per SM for a latency-bound step
+  const bool s_glob = GATED && RES && (P.variant_flags & 8);
+  const bool s_smem = GATED && RES && !s_glob;
   const size_t per_warp = (RES ? (size_t)N * HP4 * 16 : 0) +
-                          a16((size_t)(2 * W + (GATED ? (RES ? N * KW : 0) + K : 0)) * 4 + (GATED ? (size_t)K * 2 : 0));
+                          a16((size_t)(2 * W + (GATED ? (s_smem ? N * KW : 0) + K : 0)) * 4 + (GATED ? (size_t)K * 2 : 0));
   int4 *s_hq = (int4 *)(s_chain0 + (size_t)warp * per_warp);
   uint32_t *s_bits = (uint32_t *)(s_hq + (RES ? (size_t)N * HP4 : 0));
   uint32_t *s_act = s_bits + W;
   uint32_t *s_S;
-  if constexpr (RES) s_S = s_act + W;
+  if (s_smem) s_S = s_act + W;
   else s_S = P.gate_scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * N * KW;
-  uint32_t *s_list = s_act + W + (GATED && RES ? N * KW : 0);   // compacted active rows of the step (gated)
+  uint32_t *s_list = s_act + W + (s_smem ? N * KW : 0);         // compacted active rows of the step (gated)
   unsigned short *s_pos = (unsigned short *)(s_list + (GATED ? K : 0));
   for (int q = threadIdx.x; q < K * HP4; q += blockDim.x) s_W[q] = ((const int4 *)sv.W1q)[q];
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_off[k] = sv.offs[k];
@@ -232,6 +237,10 @@ __global__ void __launch_bounds__(RES ? 512 : 256, RES ? 1 : 4) sa_resident_kern
       const int f1 = fp & 0xffff, f2 = fp >> 16;
       const int f = f2 * d + f1;
       const int sgn = ((s_bits[f >> 5] >> (f & 31)) & 1) ? -1 : 1;
+      if (s_glob && ((s + 1) & 31) != 0) {         // index in global memory: the next step's words are pulled towards the SM now
+        const int fn = __shfl_sync(SO_FULL, batch.f, (int)((s + 1) & 31));
+        if (lane < KW) prefetch_l1(s_S + ((fn >> 16) * d + (fn & 0xffff)) * KW + lane);
+      }
       if constexpr (!RES) {
         // global state: pull the next step's index words and active rows towards the SM while this step computes
         // (a hint only; the draws of a batch are known 32 steps ahead)
@@ -823,25 +832,36 @@ static bool shape_ok(const so_surrogate *s, int N) {
 
 // Warps per CTA and its shared memory, maximising the resident chains of an SM; false if the state does not fit
 // (or the tree is too large to share).
-bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out, int min_warps_per_sm) {
+bool so_resident_plan(const so_surrogate *s, int N, int W, int *warps_out, size_t *smem_out, int min_warps_per_sm,
+                      int *index_global_out) {
   const size_t kSmemSM = 228 * 1024, kSmemCTA = 227 * 1024;
   const int KW = (s->K + 31) / 32;
   if (!shape_ok(s, N)) return false;
   const size_t shared = shared_tables_bytes(s);
-  const size_t per_warp = (size_t)N * s->HP4 * 16 + a16((size_t)(2 * W + (s->gated ? N * KW + s->K : 0)) * 4 + (s->gated ? (size_t)s->K * 2 : 0));
-  int best_w = 0, best_total = 0;
+  int best_w = 0, best_total = 0, best_glob = 0;
   size_t best_smem = 0;
-  const int cand[] = {4, 5, 6, 8, 10, 12, 16};
-  for (int w : cand) {
-    size_t smem = shared + (size_t)w * per_warp;
-    if (smem > kSmemCTA) continue;
-    int per_sm = (int)(kSmemSM / (smem + 1024));
-    if (per_sm * w > 64) per_sm = 64 / w;
-    if (per_sm * w > best_total) { best_total = per_sm * w; best_w = w; best_smem = smem; }
+  const int cand[] = {4, 5, 6, 7, 8, 10, 12, 14, 16};
+  // gated: the path index (N * KW words per warp) in shared memory, or in the per-warp global scratch when that fits more
+  // warps on an SM (at most 16: the kernel needs its 128 registers per thread)
+  const char *env = getenv("SO_RES_INDEX_GLOBAL");
+  for (int glob = 0; glob <= (s->gated ? 1 : 0); ++glob) {
+    if (env && s->gated && (env[0] == '1') != (glob == 1)) continue;
+    const size_t per_warp = (size_t)N * s->HP4 * 16 +
+                            a16((size_t)(2 * W + (s->gated ? (glob ? 0 : N * KW) + s->K : 0)) * 4 + (s->gated ? (size_t)s->K * 2 : 0));
+    for (int w : cand) {
+      size_t smem = shared + (size_t)w * per_warp;
+      if (smem > kSmemCTA) continue;
+      int per_sm = (int)(kSmemSM / (smem + 1024));
+      if (per_sm * w > 64) per_sm = 64 / w;
+      int total = per_sm * w;
+      if (s->gated && total > 16) total = 16;       // (register file: 16 warps of 128 registers)
+      if (total > best_total) { best_total = total; best_w = w; best_smem = smem; best_glob = glob; }
+    }
   }
   if (best_total < min_warps_per_sm) return false;   // too few resident chains to keep an SM busy: the global-memory kernels win
   if (warps_out) *warps_out = best_w;
   if (smem_out) *smem_out = best_smem;
+  if (index_global_out) *index_global_out = best_glob;
   return true;
 }
 
@@ -898,16 +918,33 @@ bool so_gate_index_ok(const so_surrogate *s, int N, int W) {
     kern<<<blocks, warps * 32, smem, st>>>(P);                                                             \
   }
 
-int so_launch_anneal_resident(const so_chains *c, const SaParams &P, cudaStream_t st) {
+int so_launch_anneal_resident(const so_chains *c, const SaParams &P0, cudaStream_t st) {
   const so_surrogate *s = c->sur;
-  int n_sm = 0, warps = 0;
+  int n_sm = 0, warps = 0, index_global = 0;
   size_t smem = 0;
   SO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
-  if (!so_resident_plan(s, P.N, P.W, &warps, &smem, 1)) { so_set_error("resident kernel: state does not fit"); return SO_EINVAL; }
+  if (!so_resident_plan(s, P0.N, P0.W, &warps, &smem, 1, &index_global)) { so_set_error("resident kernel: state does not fit"); return SO_EINVAL; }
   const int per_sm = (int)((228 * 1024) / (smem + 1024));
-  long long want = (P.n_chains + warps - 1) / warps;
+  long long want = (P0.n_chains + warps - 1) / warps;
   int blocks = (int)(want < (long long)n_sm * per_sm ? want : (long long)n_sm * per_sm);
   if (blocks < 1) blocks = 1;
+  SaParams P = P0;
+  if (index_global) {                              // path index of every resident warp in a scratch buffer of the handle
+    const size_t need = (size_t)blocks * warps * P.N * ((s->K + 31) / 32) * 4;
+    if (c->gate_scratch_bytes < need) {
+      if (c->gate_scratch) cudaFree(c->gate_scratch);
+      c->gate_scratch = nullptr;
+      c->gate_scratch_bytes = 0;
+      if (cudaMalloc(&c->gate_scratch, need) != cudaSuccess) {
+        cudaGetLastError();
+        so_set_error("out of device memory for the gate index (%zu bytes)", need);
+        return SO_ENOMEM;
+      }
+      c->gate_scratch_bytes = need;
+    }
+    P.gate_scratch = c->gate_scratch;
+    P.variant_flags |= 8;
+  }
 #define SO_RES_CASE(V) \
   case V:              \
     if (s->gated) SO_RES_LAUNCH(V, true, true) else SO_RES_LAUNCH(V, false, true) break;
